@@ -1,0 +1,12 @@
+"""CPU oracle for the MLegS transform / nonlinear-term hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mlegs_b200/`` may import this
+package; only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do.
+
+PARITY UNPINNED: the reference (Fortran 2008 + MPI + FFTE + FM + LAPACK)
+cannot be compiled in this image (no Fortran compiler, no MPI) and its own
+test-suite asserts no numeric value.  The oracle is therefore pinned only
+against the analytic known-answers listed in SURVEY.md section 4.3
+(tests/test_oracle_analytic.py); see DESIGN.md.
+"""
