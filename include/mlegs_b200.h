@@ -1,0 +1,159 @@
+/*
+ * mlegs_b200 -- C ABI of the B200-native MLegS hot path.
+ *
+ * The reference (UCBCFD/MLegS v1.1.3) has no FFI: its seam is the Fortran-2008
+ * module/submodule split (src/modules/mlegs_scalar.f90 declares the interfaces,
+ * src/submodules/mlegs_scalar_{init,dist,ops}.f90 hold the bodies; Makefile.dep:21-25).
+ * A replacement submodule keeps mlegs_scalar.f90 unchanged and forwards each
+ * `module procedure` to the entry point below that cites it (see INTEGRATION.md for
+ * the ISO_C_BINDING interface block).  "ops" = src/submodules/mlegs_scalar_ops.f90,
+ * "dist" = src/submodules/mlegs_scalar_dist.f90, "sinit" = src/submodules/mlegs_spectfm_init.f90.
+ *
+ * Conventions
+ *  - every function returns 0 on success or an MLEGS_E_* code; mlegs_b200_last_error()
+ *    then holds the reference's own `stop '...'` text for that failure.
+ *  - a field is complex(p8) e(loc_sz(1),loc_sz(2),loc_sz(3)), column-major, resident in HBM;
+ *    `e` is a device pointer owned by the library (mlegs_b200_field_alloc/free).
+ *  - no torch / C++ types cross this boundary: plain pointers, ints, doubles.
+ *  - there is no CPU fallback: without a CUDA device every compute entry fails with
+ *    MLEGS_E_CUDA.
+ */
+#ifndef MLEGS_B200_H
+#define MLEGS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  MLEGS_OK = 0,
+  MLEGS_E_ARG = 1,      /* precondition failure -> the reference's `stop '<msg>'`        */
+  MLEGS_E_STATE = 2,    /* library not initialised / wrong space                          */
+  MLEGS_E_CUDA = 3,     /* CUDA runtime error (includes "no device")                      */
+  MLEGS_E_COMM = 201,   /* reference error_flag_comm (modules/mlegs_envir.f90:40)         */
+  MLEGS_E_MISC = 205    /* reference error_flag_misc: non-finite state (check_stability)  */
+};
+
+/* modules/mlegs_base.f90 globals that the hot path reads */
+typedef struct mlegs_params {
+  int nr, np, nz;
+  int nrchop, npchop, nzchop;
+  double ell, zlen;
+  double visc;
+  int hyperpow;
+  double hypervisc;
+  int is_svv;
+  double svv_cutoff, svv_target, svv_strength, svv_relax;
+} mlegs_params;
+
+/* mirror of type(scalar), modules/mlegs_scalar.f90:15-49.  Updated in place. */
+typedef struct mlegs_field {
+  void *e;                 /* device pointer, complex(p8), column-major loc_sz              */
+  int glb_sz[3], loc_sz[3], loc_st[3], axis_comm[3];
+  double ln;
+  int nrchop_offset, npchop_offset, nzchop_offset;
+  char space[4];           /* "PPP","PFP","FFP","FFF" (+"PFF" inside vec2tp), NUL-terminated */
+} mlegs_field;
+
+/* ---- library / device ---------------------------------------------------------------- */
+const char *mlegs_b200_last_error(void);
+int mlegs_b200_version(void);
+/* cudaStream_t the library launches on (NULL = legacy default stream). */
+int mlegs_b200_set_stream(void *cuda_stream);
+int mlegs_b200_device_sync(void);
+/* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
+long long mlegs_b200_launch_count(int reset);
+
+/* ---- transform kit: host tables (tfm%init(), sinit:6-154) ---------------------------- */
+/* sizes: x,w,ln,r: nr;  lognorm: (nrchop+14)*npchop;  pf: (nr/2)*(nrchop+14)*npchop;
+ * at0,at1: nrchop;  ak: nz.  All column-major like the Fortran arrays.  Host code, runs the
+ * three-term recurrence in binary128 where the reference uses 50-digit FM.                 */
+int mlegs_b200_tfm_tables(const mlegs_params *p, double *x, double *w, double *ln, double *r,
+                          double *lognorm, double *pf, double *at0, double *at1, double *ak);
+
+/* Upload the kit once; tables stay resident in HBM (replaces the host-side use of the global
+ * `tfm` by ops:*).  rank/nranks describe the slab decomposition (dist:508-578 with
+ * dims = (/nranks,1/)); peer buffers are attached later by mlegs_b200_dist_attach.       */
+int mlegs_b200_init(const mlegs_params *p, const double *x, const double *w,
+                    const double *lognorm, const double *pf, const double *at0,
+                    const double *at1, int rank, int nranks);
+int mlegs_b200_finalize(void);
+int mlegs_b200_update_params(const mlegs_params *p);   /* visc, hypervisc, svv_* only */
+
+/* ---- scalar storage: scalar_init / dealloc / copy (mlegs_scalar_init.f90:6-140) ------ */
+/* space3 selects the layout: "PPP" -> axis_comm (1,0,2) (r sharded), anything else ->
+ * (2,1,0) (m sharded); on one rank both are the full (nrdim,npdim,nzdim) block.           */
+int mlegs_b200_field_alloc(mlegs_field *f, const char *space3);
+int mlegs_b200_field_free(mlegs_field *f);
+int mlegs_b200_field_copy(mlegs_field *dst, const mlegs_field *src);      /* assignment(=) */
+int mlegs_b200_field_zero(mlegs_field *f);
+int mlegs_b200_field_upload(mlegs_field *f, const void *host_e);          /* whole local block */
+int mlegs_b200_field_download(const mlegs_field *f, void *host_e);
+int mlegs_b200_field_chop_offset(mlegs_field *f, int iof1, int iof2, int iof3);
+/* pinned host staging (cudaHostRegister) for the host-buffer entry points below */
+int mlegs_b200_host_register(void *host_ptr, size_t bytes);
+int mlegs_b200_host_unregister(void *host_ptr);
+
+/* ---- spectral transforms ------------------------------------------------------------- */
+int mlegs_b200_trans(mlegs_field *s, const char to[3]);                   /* ops:157-235 */
+/* Reference-facing call on a HOST array (the Fortran s%e): H2D, trans, D2H. */
+int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], double ln);
+/* scalar_exchange, dist:6-67 (slab layout: only (2,1)/(1,2) move data) */
+int mlegs_b200_exchange(mlegs_field *s, int axis_old, int axis_new);
+
+/* ---- masks / filters / far field ----------------------------------------------------- */
+int mlegs_b200_chop(mlegs_field *s);                                      /* ops:6-41    */
+int mlegs_b200_dealias(mlegs_field *s);                                   /* ops:43-70   */
+int mlegs_b200_svv_filter(mlegs_field *s, double *gain);                  /* ops:72-155  */
+int mlegs_b200_calcat0(const mlegs_field *s, double *out_nz_complex);     /* ops:237-272 */
+int mlegs_b200_calcat1(const mlegs_field *s, double *out_nz_complex);     /* ops:274-309 */
+int mlegs_b200_zeroat1(mlegs_field *s);                                   /* ops:311-325 */
+
+/* ---- spectral differential operators and solves -------------------------------------- */
+int mlegs_b200_delsqp(mlegs_field *s);                                    /* ops:327-366 */
+int mlegs_b200_idelsqp(mlegs_field *s);                                   /* ops:368-416 */
+int mlegs_b200_xxdx(mlegs_field *s);                                      /* ops:418-463 */
+int mlegs_b200_del2h(mlegs_field *s);                                     /* ops:465-518 */
+int mlegs_b200_del2(mlegs_field *s);                                      /* ops:520-573 */
+int mlegs_b200_idel2(mlegs_field *s, int have_preln, double preln);       /* ops:575-760 */
+int mlegs_b200_ihelm(mlegs_field *s, double alpha);                       /* ops:791-854 */
+int mlegs_b200_helmp(mlegs_field *s, int power, double alpha, double beta);   /* ops:856-903 */
+int mlegs_b200_ihelmp(mlegs_field *s, int power, double alpha, double beta);  /* ops:905-1000 */
+
+/* ---- time integrators ---------------------------------------------------------------- */
+int mlegs_b200_fefe(mlegs_field *s, const mlegs_field *nl, double dt);    /* ops:1065-1094 */
+int mlegs_b200_febe(mlegs_field *s, const mlegs_field *nl, double dt);    /* ops:1157-1198 */
+int mlegs_b200_abcn(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl,
+                    mlegs_field *nl_p, double dt);                        /* ops:1200-1262 */
+
+/* ---- vector-field operations --------------------------------------------------------- */
+int mlegs_b200_vecprod(mlegs_field *vr, mlegs_field *vp, mlegs_field *vz,
+                       const mlegs_field *ur, const mlegs_field *up,
+                       const mlegs_field *uz);                            /* ops:1264-1306 */
+int mlegs_b200_vec2tp(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field *vz,
+                      mlegs_field *psi, mlegs_field *chi);                /* ops:1308-1453 */
+int mlegs_b200_tp2vec(const mlegs_field *psi, const mlegs_field *chi,
+                      mlegs_field *vr, mlegs_field *vp, mlegs_field *vz); /* ops:1455-1545 */
+int mlegs_b200_tp2curlvec(const mlegs_field *psi, const mlegs_field *chi,
+                          mlegs_field *wr, mlegs_field *wp, mlegs_field *wz); /* ops:1547-1560 */
+
+/* ---- whole-array helpers the apps do with Fortran array syntax on s%e ---------------- */
+/* y%e = a*x%e + b*y%e (e.g. apps/vortical_flow_3d.f90:136-137, 379) */
+int mlegs_b200_axpby(mlegs_field *y, double a, const mlegs_field *x, double b);
+/* all(ieee_is_finite(s%e)) -- check_stability, apps/vortical_flow_3d.f90:397-409 */
+int mlegs_b200_is_finite(const mlegs_field *s, int *all_finite);
+
+/* ---- multi-GPU (one process per GPU, slab over m) ------------------------------------ */
+/* CUDA-IPC plumbing for the fused FFT+transpose kernels: each rank exports the handle of its
+ * exchange window, the host side all-gathers the 64-byte handles (torch.distributed / MPI)
+ * and attaches them.  Replaces MPI_Alltoallw + derived datatypes (dist:468-504).            */
+int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64[64]);
+int mlegs_b200_dist_attach(const unsigned char *handles64_all_ranks);
+int mlegs_b200_dist_detach(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLEGS_B200_H */

@@ -1,0 +1,195 @@
+// trans(): the PPP <-> PFP <-> FFP <-> FFF state machine of
+// /root/reference/src/submodules/mlegs_scalar_ops.f90:157-235, composed from the FFT and Legendre
+// kernels.  On one rank the two scalar_exchange calls are pure re-labellings (the block already is
+// the whole (nrdim, npdim, nzdim) array); on several ranks the (2,1)/(1,2) exchange is the
+// all-to-all in dist.cu and the (1,3)/(3,1) exchange is a no-op in the slab layout.
+#include <cstring>
+
+#include "kernels.h"
+
+namespace mlegs {
+
+int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, void *dst);   // dist.cu
+
+static int space_id(const char *sp) {
+  if (!strncmp(sp, "PPP", 3)) return 0;
+  if (!strncmp(sp, "PFP", 3)) return 1;
+  if (!strncmp(sp, "FFP", 3)) return 2;
+  if (!strncmp(sp, "FFF", 3)) return 3;
+  return -1;
+}
+static const char *kSpaceName[4] = {"PPP", "PFP", "FFP", "FFF"};
+
+static void set_space(mlegs_field *s, int id) {
+  memcpy(s->space, kSpaceName[id], 3);
+  s->space[3] = 0;
+}
+
+static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
+  Context &c = ctx();
+  int nrc = c.p.nrchop + s->nrchop_offset;
+  int npc = c.p.npchop + s->npchop_offset;
+  if (nrc > c.nrdim) return fail(MLEGS_E_ARG, std::string(who) + ": chopping in r too large");
+  if (npc > c.npdim) return fail(MLEGS_E_ARG, std::string(who) + ": chopping in p too large");
+  a->pf = c.d_pf;
+  a->w = c.d_w;
+  a->lnx = c.d_lnx;
+  a->nr = c.p.nr;
+  a->nrh = c.nrh;
+  a->ne = c.ne;
+  a->nrl = s->loc_sz[0];
+  a->npl = s->loc_sz[1];
+  a->m0 = s->loc_st[1];
+  a->nzl = s->loc_sz[2];
+  a->nrc = nrc;
+  a->npc = npc;
+  a->nrdim = c.nrdim;
+  a->lnval = s->ln;
+  return MLEGS_OK;
+}
+
+// One stage, reading `src` and writing `dst` (may be equal for the FFT stages).
+int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+  Context &c = ctx();
+  cudaStream_t st = (cudaStream_t)c.stream;
+  long long rows = s->loc_sz[0];
+  return launch_fft_lines(forward ? FFT_R2C_FWD : FFT_C2R_BWD, c.plan_p, src, dst, rows, rows, s->loc_sz[2],
+                          rows * (long long)s->loc_sz[1], c.d_tw_p, c.p.np, forward ? 1.0 / c.p.np : 1.0, st);
+}
+
+int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+  Context &c = ctx();
+  cudaStream_t st = (cudaStream_t)c.stream;
+  long long plane = (long long)s->loc_sz[0] * s->loc_sz[1];
+  return launch_fft_lines(forward ? FFT_C2C_FWD : FFT_C2C_BWD, c.plan_z, src, dst, plane, plane, 1, 0, c.d_tw_z,
+                          c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st);
+}
+
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+  LegArgs a;
+  MLEGS_TRY(rtrans_args(s, forward ? "rtrans_forward" : "rtrans_backward", &a));
+  a.in = src;
+  a.out = dst;
+  cudaStream_t st = (cudaStream_t)ctx().stream;
+  return forward ? launch_leg_forward(a, st) : launch_leg_backward(a, st);
+}
+
+int trans_impl(mlegs_field *s, const char *to) {
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  int cur = space_id(s->space), dst = space_id(to);
+  if (cur < 0)
+    return fail(MLEGS_E_ARG, "trans: scalar space info corrupted (only accepting PPP, PFP, FFP and FFF)");
+  if (dst < 0) return fail(MLEGS_E_ARG, "trans: only taking PPP, PFP, FFP and FFF for spectral transformation");
+  if (cur == dst) return MLEGS_OK;
+  cudaStream_t st = (cudaStream_t)c.stream;
+  const bool has_p = c.p.np > 1, has_z = c.p.nz > 1;
+  const bool multi = c.nranks > 1 && has_p;
+
+  cplx *home = (cplx *)s->e;
+  cplx *tmp = (cplx *)c.d_scratch[0];
+  cplx *at = home;   // where the data currently lives
+  auto other = [&](cplx *p) { return p == home ? tmp : home; };
+
+  if (cur < dst) {   // forward, ops:185-208
+    while (cur < dst) {
+      if (cur == 0) {
+        if (has_p) {
+          if (multi) {
+            // FFT in place, then the (2,1) exchange moves the block into the other buffer
+            MLEGS_TRY(stage_phi(s, true, at, at));
+            MLEGS_TRY(exchange_slab(s, 2, 1, at, other(at)));
+            at = other(at);
+          } else {
+            // without an axial stage, go out of place so that the Legendre stage lands back at home
+            cplx *o = (!has_z && dst >= 2) ? other(at) : at;
+            MLEGS_TRY(stage_phi(s, true, at, o));
+            at = o;
+          }
+        }
+      } else if (cur == 1) {
+        MLEGS_TRY(stage_r(s, true, at, other(at)));   // ln removal (ops:193-195) is fused into the load
+        at = other(at);
+      } else if (cur == 2) {
+        if (has_z) {
+          cplx *o = (at == home) ? at : home;   // land at home whenever possible
+          MLEGS_TRY(stage_z(s, true, at, o));
+          at = o;
+        }
+      }
+      ++cur;
+      set_space(s, cur);
+    }
+  } else {           // backward, ops:210-233
+    while (cur > dst) {
+      if (cur == 3) {
+        if (has_z) {
+          // if the Legendre stage follows, go out of place so that it lands back at home
+          cplx *o = (dst <= 1) ? other(at) : at;
+          MLEGS_TRY(stage_z(s, false, at, o));
+          at = o;
+        }
+      } else if (cur == 2) {
+        MLEGS_TRY(stage_r(s, false, at, other(at)));  // + ln term (ops:219-221) fused into the epilogue
+        at = other(at);
+      } else if (cur == 1) {
+        if (has_p) {
+          if (multi) {
+            MLEGS_TRY(exchange_slab(s, 1, 2, at, other(at)));
+            at = other(at);
+            cplx *o = home;
+            MLEGS_TRY(stage_phi(s, false, at, o));
+            at = o;
+          } else {
+            cplx *o = home;
+            MLEGS_TRY(stage_phi(s, false, at, o));
+            at = o;
+          }
+        }
+      }
+      --cur;
+      set_space(s, cur);
+    }
+  }
+  if (at != home) {
+    size_t n = (size_t)s->loc_sz[0] * s->loc_sz[1] * s->loc_sz[2];
+    CUDA_TRY(cudaMemcpyAsync(home, at, n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  }
+  return MLEGS_OK;
+}
+
+}  // namespace mlegs
+
+using namespace mlegs;
+
+extern "C" {
+
+int mlegs_b200_trans(mlegs_field *s, const char to[3]) { return trans_impl(s, to); }
+
+int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], double ln) {
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  cudaStream_t st = (cudaStream_t)c.stream;
+  static mlegs_field f;   // staging scalar, allocated on first use
+  static size_t f_bytes = 0;
+  if (space_id(from) < 0)
+    return fail(MLEGS_E_ARG, "trans: scalar space info corrupted (only accepting PPP, PFP, FFP and FFF)");
+  if (!f.e || f_bytes != c.field_bytes) {
+    if (f.e) cudaFree(f.e);
+    CUDA_TRY(cudaMalloc(&f.e, c.field_bytes));
+    f_bytes = c.field_bytes;
+  }
+  field_set_layout(&f, space_id(from) == 0);
+  f.nrchop_offset = f.npchop_offset = f.nzchop_offset = 0;
+  set_space(&f, space_id(from));
+  f.ln = ln;
+  size_t n = (size_t)f.loc_sz[0] * f.loc_sz[1] * f.loc_sz[2];
+  CUDA_TRY(cudaMemcpyAsync(f.e, host_e, n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+  MLEGS_TRY(trans_impl(&f, to));
+  n = (size_t)f.loc_sz[0] * f.loc_sz[1] * f.loc_sz[2];
+  CUDA_TRY(cudaMemcpyAsync(host_e, f.e, n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MLEGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+"""Host mirror of type(scalar) and of the operator interfaces of modules/mlegs_scalar.f90.
+
+Every function forwards to the C-ABI entry point of the same name; data stay in HBM.
+Names, argument meaning and error text follow the reference's interfaces
+(modules/mlegs_scalar.f90:115-428) so tests read like the reference's tutorials.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Field, check
+
+
+class Scalar:
+    """type(scalar): a distributed complex field resident on the device."""
+
+    def __init__(self, space: str = "PPP"):
+        self.f = Field()
+        check(_lib.lib().mlegs_b200_field_alloc(C.byref(self.f), space.encode()))
+
+    # -- metadata ------------------------------------------------------------------------
+    @property
+    def space(self) -> str:
+        return self.f.space.decode()
+
+    @space.setter
+    def space(self, v: str):
+        self.f.space = v.encode()
+
+    @property
+    def ln(self) -> float:
+        return self.f.ln
+
+    @ln.setter
+    def ln(self, v: float):
+        self.f.ln = float(v)
+
+    @property
+    def loc_sz(self):
+        return tuple(self.f.loc_sz)
+
+    @property
+    def loc_st(self):
+        return tuple(self.f.loc_st)
+
+    @property
+    def glb_sz(self):
+        return tuple(self.f.glb_sz)
+
+    def chop_offset(self, iof1: int, iof2: int = 0, iof3: int = 0):
+        check(_lib.lib().mlegs_b200_field_chop_offset(C.byref(self.f), iof1, iof2, iof3))
+
+    # -- data movement ------------------------------------------------------------------------
+    def upload(self, host: np.ndarray) -> "Scalar":
+        a = np.asfortranarray(host, dtype=np.complex128)
+        if a.shape != self.loc_sz:
+            raise ValueError(f"scalar upload: shape {a.shape} != local size {self.loc_sz}")
+        check(_lib.lib().mlegs_b200_field_upload(C.byref(self.f), a.ctypes.data_as(C.c_void_p)))
+        return self
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.loc_sz, dtype=np.complex128, order="F")
+        check(_lib.lib().mlegs_b200_field_download(C.byref(self.f), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def copy(self) -> "Scalar":
+        o = Scalar.__new__(Scalar)
+        o.f = Field()
+        check(_lib.lib().mlegs_b200_field_copy(C.byref(o.f), C.byref(self.f)))
+        return o
+
+    def assign(self, other: "Scalar"):
+        """this = that (scalar_copy, submodules/mlegs_scalar_init.f90:106-140)."""
+        check(_lib.lib().mlegs_b200_field_copy(C.byref(self.f), C.byref(other.f)))
+
+    def zero(self):
+        check(_lib.lib().mlegs_b200_field_zero(C.byref(self.f)))
+
+    def exchange(self, axis_old: int, axis_new: int):
+        check(_lib.lib().mlegs_b200_exchange(C.byref(self.f), axis_old, axis_new))
+
+    def dealloc(self):
+        if self.f.e:
+            check(_lib.lib().mlegs_b200_field_free(C.byref(self.f)))
+
+    def __del__(self):
+        try:
+            self.dealloc()
+        except Exception:
+            pass
+
+
+def _l():
+    return _lib.lib()
+
+
+def trans(s: Scalar, space: str):
+    check(_l().mlegs_b200_trans(C.byref(s.f), space.encode()))
+
+
+def trans_host(host_e: np.ndarray, from_space: str, to_space: str, ln: float = 0.0):
+    """Reference-facing call on a host array (the Fortran s%e): H2D + trans + D2H."""
+    assert host_e.flags.f_contiguous and host_e.dtype == np.complex128
+    check(_l().mlegs_b200_trans_host(host_e.ctypes.data_as(C.c_void_p), from_space.encode(), to_space.encode(), ln))
+
+
+def chop(s): check(_l().mlegs_b200_chop(C.byref(s.f)))
+def dealias(s): check(_l().mlegs_b200_dealias(C.byref(s.f)))
+
+
+def svv_filter(s, gain: float) -> float:
+    g = C.c_double(gain)
+    check(_l().mlegs_b200_svv_filter(C.byref(s.f), C.byref(g)))
+    return g.value
+
+
+def _calcat(fn, s):
+    out = np.zeros(s.glb_sz[2], dtype=np.complex128)
+    check(fn(C.byref(s.f), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def calcat0(s): return _calcat(_l().mlegs_b200_calcat0, s)
+def calcat1(s): return _calcat(_l().mlegs_b200_calcat1, s)
+def zeroat1(s): check(_l().mlegs_b200_zeroat1(C.byref(s.f)))
+def delsqp(s): check(_l().mlegs_b200_delsqp(C.byref(s.f)))
+def idelsqp(s): check(_l().mlegs_b200_idelsqp(C.byref(s.f)))
+def xxdx(s): check(_l().mlegs_b200_xxdx(C.byref(s.f)))
+def del2h(s): check(_l().mlegs_b200_del2h(C.byref(s.f)))
+def del2(s): check(_l().mlegs_b200_del2(C.byref(s.f)))
+
+
+def idel2(s, preln=None):
+    if preln is None:
+        check(_l().mlegs_b200_idel2(C.byref(s.f), 0, 0.0))
+    else:
+        check(_l().mlegs_b200_idel2(C.byref(s.f), 1, float(preln)))
+
+
+def ihelm(s, alpha): check(_l().mlegs_b200_ihelm(C.byref(s.f), alpha))
+def helmp(s, power, alpha, beta): check(_l().mlegs_b200_helmp(C.byref(s.f), power, alpha, beta))
+def ihelmp(s, power, alpha, beta): check(_l().mlegs_b200_ihelmp(C.byref(s.f), power, alpha, beta))
+def fefe(s, nl, dt): check(_l().mlegs_b200_fefe(C.byref(s.f), C.byref(nl.f), dt))
+def febe(s, nl, dt): check(_l().mlegs_b200_febe(C.byref(s.f), C.byref(nl.f), dt))
+
+
+def abcn(s, s_p, nl, nl_p, dt):
+    check(_l().mlegs_b200_abcn(C.byref(s.f), C.byref(s_p.f), C.byref(nl.f), C.byref(nl_p.f), dt))
+
+
+def vecprod(vr, vp, vz, ur, up, uz):
+    check(_l().mlegs_b200_vecprod(C.byref(vr.f), C.byref(vp.f), C.byref(vz.f), C.byref(ur.f), C.byref(up.f),
+                                  C.byref(uz.f)))
+
+
+def vec2tp(vr, vp, vz, psi, chi):
+    check(_l().mlegs_b200_vec2tp(C.byref(vr.f), C.byref(vp.f), C.byref(vz.f), C.byref(psi.f), C.byref(chi.f)))
+
+
+def tp2vec(psi, chi, vr, vp, vz):
+    check(_l().mlegs_b200_tp2vec(C.byref(psi.f), C.byref(chi.f), C.byref(vr.f), C.byref(vp.f), C.byref(vz.f)))
+
+
+def tp2curlvec(psi, chi, wr, wp, wz):
+    check(_l().mlegs_b200_tp2curlvec(C.byref(psi.f), C.byref(chi.f), C.byref(wr.f), C.byref(wp.f), C.byref(wz.f)))
+
+
+def axpby(y, a, x, b): check(_l().mlegs_b200_axpby(C.byref(y.f), a, C.byref(x.f), b))
+
+
+def is_finite(s) -> bool:
+    v = C.c_int(0)
+    check(_l().mlegs_b200_is_finite(C.byref(s.f), C.byref(v)))
+    return bool(v.value)
+
+
+def device_sync(): check(_l().mlegs_b200_device_sync())
+def set_stream(ptr): check(_l().mlegs_b200_set_stream(C.c_void_p(ptr)))
+def launch_count(reset=False) -> int: return int(_l().mlegs_b200_launch_count(int(reset)))

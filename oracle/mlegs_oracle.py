@@ -101,9 +101,24 @@ def leg_lognorm(ndim: int, ms) -> np.ndarray:
     return out
 
 
+def _libm_lgamma():
+    """gfortran's log_gamma is glibc's lgamma; CPython's math.lgamma is its own Lanczos code and
+    differs by a few ulp, which exp() turns into ~1e-13 relative table differences."""
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    fn = libm.lgamma
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_double]
+    return fn
+
+
+_lgamma = _libm_lgamma()
+
+
 def log_fact(m: int) -> float:
     """sinit:351-357."""
-    return math.lgamma(2 * m + 1.0) - m * math.log(2.0) - math.lgamma(m + 1.0)
+    return _lgamma(2 * m + 1.0) - m * math.log(2.0) - _lgamma(m + 1.0)
 
 
 def leg_tbl(x, ne: int, ms, lnrm: np.ndarray, digits: int = 50) -> np.ndarray:

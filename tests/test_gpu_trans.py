@@ -1,0 +1,110 @@
+"""GPU parity of the spectral transforms (trans, ops:157-235) against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import mlegs_b200 as mb
+from oracle import mlegs_oracle as mo
+from helpers import oracle_kit, random_fff, random_ppp, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+# (nr, np, nz, nrchop, npchop, nzchop, ell, hyperpow)
+CASES = {
+    "gate2d": (32, 48, 1, 32, 25, 1, 1.0, 0),          # tools/validate_tutorials.py:255-269
+    "gate2d_nr64": (64, 48, 1, 64, 25, 1, 1.0, 0),     # BASELINE.json configs[0] as quoted (NR=64)
+    "gate3d": (32, 16, 8, 32, 9, 5, 4.0, 8),           # tools/validate_tutorials.py:222-238
+    "radix35": (36, 30, 20, 30, 12, 9, 2.0, 4),        # np, nz with factors 3 and 5; chops below the maximum
+    "cube64": (64, 64, 64, 64, 33, 33, 4.0, 0),
+}
+TOL = 1.0e-12   # BASELINE.json north_star: 1e-12 relative L2 per transform
+
+
+def _setup(case):
+    nr, np_, nz, nrc, npc, nzc, ell, hp = CASES[case]
+    p = mb.make_params(nr, np_, nz, nrc, npc, nzc, ell=ell, zlen=2 * np.pi, hyperpow=hp,
+                       hypervisc=(1e-6 if hp else 0.0))
+    kit = mb.TfmKit.init(p)
+    return kit, oracle_kit(kit)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_stagewise_forward_and_backward(case):
+    kit, ok = _setup(case)
+    e0 = random_ppp(ok, seed=1)
+    s = mb.Scalar("PPP").upload(e0)
+    so = mo.Scalar(e=e0.copy(order="F"), space="PPP")
+    for sp in ("PFP", "FFP", "FFF", "FFP", "PFP", "PPP"):
+        mb.trans(s, sp)
+        mo.trans(so, sp, ok)
+        assert s.space == sp
+        got = s.download()
+        assert rel_l2(got, so.e) < TOL, (case, sp)
+        # continue both chains from the oracle's state so that stage errors do not accumulate
+        s.upload(so.e)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_full_transforms_and_ln_term(case):
+    kit, ok = _setup(case)
+    e0 = random_fff(ok, seed=2)
+    for ln in (0.0, 0.37):
+        s = mb.Scalar("FFF").upload(e0)
+        s.ln = ln
+        so = mo.Scalar(e=e0.copy(order="F"), space="FFF", ln=ln)
+        mb.trans(s, "PPP")
+        mo.trans(so, "PPP", ok)
+        assert rel_l2(s.download(), so.e) < TOL
+        mb.trans(s, "FFF")
+        mo.trans(so, "FFF", ok)
+        assert rel_l2(s.download(), so.e) < TOL
+        assert rel_l2(s.download(), e0) < 50 * TOL     # forward(backward(x)) == x up to the GL quadrature error
+
+
+def test_chop_offsets_in_rtrans():
+    kit, ok = _setup("gate3d")
+    e0 = random_ppp(ok, seed=3)
+    s = mb.Scalar("PPP").upload(e0)
+    so = mo.Scalar(e=e0.copy(order="F"), space="PPP")
+    s.chop_offset(3)
+    so.chop_offset(3)
+    mb.trans(s, "FFF")
+    mo.trans(so, "FFF", ok)
+    assert rel_l2(s.download(), so.e) < TOL
+    s.chop_offset(kit.nrdim)        # nrc > nrdim
+    with pytest.raises(mb.MlegsError, match="rtrans_backward: chopping in r too large"):
+        mb.trans(s, "PPP")
+
+
+def test_trans_rejects_bad_space():
+    kit, ok = _setup("gate2d")
+    s = mb.Scalar("PPP")
+    with pytest.raises(mb.MlegsError, match="only taking PPP, PFP, FFP and FFF"):
+        mb.trans(s, "XYZ")
+    s.space = "PPF"
+    with pytest.raises(mb.MlegsError, match="scalar space info corrupted"):
+        mb.trans(s, "FFF")
+
+
+def test_roundtrip_128_config_and_host_entry():
+    """BASELINE.json configs[1]: 3D scalar PPP<->FFF round trip, NR=NP=NZ=128 (SURVEY.md section 8d input 2)."""
+    p = mb.make_params(128, 128, 128, 128, 65, 65, ell=4.0, zlen=2 * np.pi, hyperpow=0)
+    kit = mb.TfmKit.init(p)
+    ok = oracle_kit(kit)
+    e0 = random_fff(ok, seed=0)
+    s = mb.Scalar("FFF").upload(e0)
+    so = mo.Scalar(e=e0.copy(order="F"), space="FFF")
+    mb.trans(s, "PPP")
+    mo.trans(so, "PPP", ok)
+    ppp = so.e.copy(order="F")
+    assert rel_l2(s.download(), ppp) < TOL
+    mb.trans(s, "FFF")
+    mo.trans(so, "FFF", ok)
+    assert rel_l2(s.download(), so.e) < TOL
+    assert rel_l2(s.download(), e0) < 50 * TOL
+    # the reference-facing host-buffer call gives the same numbers
+    h = e0.copy(order="F")
+    mb.trans_host(h, "FFF", "PPP")
+    assert rel_l2(h, ppp) < TOL
+    mb.trans_host(h, "PPP", "FFF")
+    assert rel_l2(h, so.e) < TOL
+    assert mb.launch_count() > 0
