@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- transform round-trip throughput (GDOF/s) of the MLegS hot path on B200.
+
+Workload (BASELINE.json configs[1]): 3-D scalar PPP<->FFF transform round trip at NR=NP=NZ=128
+(NRCHOP=128, NPCHOP=NZCHOP=65, L=4, ZLEN=2*pi; SURVEY.md section 8d input 2).  A "step" is one
+forward + one backward transform of every field of a batch of NF distinct fields; NF is chosen so
+the batch (NF x 17.4 MB) is larger than the 126 MB L2, i.e. consecutive kernels never find their
+input in cache ("inputs larger than L2").  GDOF/s = NF*NR*NP*NZ / t_step / 1e9.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--size S]
+
+N > 1 is launched by torchrun, one rank per GPU; fields are independent scalars, so the batch is
+sharded across ranks with no data-path collective (weak scaling: NF fields per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "transform_roundtrip_gdofs"
+UNIT = "GDOF/s"
+
+
+def workload(size: int):
+    return dict(nr=size, np=size, nz=size, nrchop=size, npchop=size // 2 + 1, nzchop=size // 2 + 1,
+                ell=4.0, zlen=2.0 * np.pi)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference path (bench's cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_roundtrip_rate(kit_tables, params, nfields: int, nthreads: int, reps: int):
+    """Round trips per second of the NumPy oracle on `nthreads` host threads (one field per thread,
+    BLAS pinned to one thread each so threads are the only parallelism)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import mlegs_oracle as mo
+    from helpers import random_fff
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:   # pragma: no cover
+        threadpool_limits = None
+    okit = mo.kit_init(params, tables=kit_tables)
+    base = mo.Scalar(e=random_fff(okit, seed=0), space="FFF")
+    mo.trans(base, "PPP", okit)
+    fields = [base.copy() for _ in range(nfields)]
+
+    def work(s):
+        mo.trans(s, "FFF", okit)
+        mo.trans(s, "PPP", okit)
+
+    def run():
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(work, fields))
+        return time.perf_counter() - t0
+
+    import contextlib
+    with (threadpool_limits(limits=1) if threadpool_limits else contextlib.nullcontext()):
+        run()   # warm-up (FFT plans, page faults)
+        ts = [run() for _ in range(reps)]
+    t = min(ts)
+    return nfields / t, t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Fortran/MPI reference cannot be
+    compiled in this image) on all host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mlegs_b200 as mb
+    from helpers import oracle_params
+    wl = workload(args.size)
+    p = mb.make_params(wl["nr"], wl["np"], wl["nz"], wl["nrchop"], wl["npchop"], wl["nzchop"], ell=wl["ell"],
+                       zlen=wl["zlen"])
+    kit = mb.TfmKit.build_tables(p)          # host-only table build (no GPU work)
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, 64)
+    nfields = nthreads
+    dof = wl["nr"] * wl["np"] * wl["nz"]
+    # warm-up + timed steps, each a bounded sample: one round trip per thread
+    per_step = []
+    for i in range(args.warmup + args.steps):
+        rate, t = cpu_roundtrip_rate(kit.tables(), oracle_params(p), nfields, nthreads, reps=1)
+        if i >= args.warmup:
+            per_step.append((rate, t))
+    rate = float(np.mean([r for r, _ in per_step]))
+    val = rate * dof / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([t for _, t in per_step]) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"PPP<->FFF round trip {args.size}^3 (BASELINE.json configs[1])",
+                       "fields_per_step": nfields, **{k: (float(v) if isinstance(v, float) else v) for k, v in wl.items()}},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port",
+                             "sample": f"{nfields} fields x 1 round trip per step, NumPy oracle port "
+                                       "(pocketfft + BLAS), one field per thread"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import mlegs_b200 as mb
+    from helpers import oracle_kit, oracle_params, random_fff
+    from oracle import mlegs_oracle as mo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = workload(args.size)
+    p = mb.make_params(wl["nr"], wl["np"], wl["nz"], wl["nrchop"], wl["npchop"], wl["nzchop"], ell=wl["ell"],
+                       zlen=wl["zlen"])
+    kit = mb.TfmKit.init(p)
+    dof = wl["nr"] * wl["np"] * wl["nz"]
+    field_bytes = int(np.prod(kit.glb_sz)) * 16
+    nf = args.fields or max(2, int(np.ceil(2.2 * 126e6 / field_bytes)))   # batch > 2x L2
+    stream = torch.cuda.Stream()
+    mb.set_stream(stream.cuda_stream)
+
+    okit = oracle_kit(kit)
+    e0 = mo.Scalar(e=random_fff(okit, seed=rank), space="FFF")
+    fields = []
+    with torch.cuda.stream(stream):
+        s0 = mb.Scalar("FFF").upload(e0.e)
+        mb.trans(s0, "PPP")
+        fields.append(s0)
+        for _ in range(nf - 1):
+            fields.append(s0.copy())
+    mb.device_sync()
+
+    def step():
+        for s in fields:
+            mb.trans(s, "FFF")
+            mb.trans(s, "PPP")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    mb.launch_count(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = mb.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * nf * dof / (ms_step * 1e-3) / 1e9
+
+    # ---- per-kernel CUDA-event timing of the same workload (separate pass, not the headline number) ----
+    mb.prof_enable(True)
+    for _ in range(2):
+        step()
+    prof = mb.prof_report()
+    mb.prof_enable(False)
+    tot = sum(v["ms"] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    dur_ms = prof[dom]["ms"] / prof[dom]["launches"]
+    nr, npn, nz = wl["nr"], wl["np"], wl["nz"]
+    nrdim, npdim = kit.glb_sz[0], kit.glb_sz[1]
+    S = sum(max(wl["nrchop"] - m, 0) for m in range(wl["npchop"]))
+    # algorithmic bytes per launch (stated in DESIGN.md)
+    alg_bytes = {
+        "fft_phi_forward": 8 * nr * npn * nz + 16 * nr * npdim * nz,
+        "fft_phi_backward": 8 * nr * npn * nz + 16 * nr * npdim * nz,
+        "fft_z_forward": 2 * 16 * nz * S,
+        "fft_z_backward": 2 * 16 * nz * S,
+        "legendre_forward": 16 * nr * wl["npchop"] * nz + 16 * S * nz,
+        "legendre_backward": 16 * nr * wl["npchop"] * nz + 16 * S * nz,
+    }
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes[dom] / (dur_ms * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": dur_ms, "share_of_step": prof[dom]["ms"] / tot,
+                "kernels": {k: {"avg_ms": v["ms"] / v["launches"], "share": v["ms"] / tot,
+                                "alg_GBps": alg_bytes[k] / (v["ms"] / v["launches"] * 1e-3) / 1e9,
+                                "legendre_TFLOPs": (2.0 * nr * nz * S / (v["ms"] / v["launches"] * 1e-3) / 1e12
+                                                    if k.startswith("legendre") else None)}
+                            for k, v in prof.items()}}
+
+    # ---- e2e: the reference-facing host-buffer entry, pinned host arrays, H2D+D2H inside the timed region ----
+    hosts = []
+    for s in fields:
+        h = torch.empty(int(np.prod(kit.glb_sz)) * 2, dtype=torch.float64).pin_memory()
+        a = h.numpy().view(np.complex128).reshape(kit.glb_sz, order="F")
+        a[...] = s.download()
+        hosts.append((h, a))
+
+    def e2e_step():
+        for _, a in hosts:
+            mb.trans_host(a, "PPP", "FFF")
+            mb.trans_host(a, "FFF", "PPP")
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": world * nf * dof / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nf * field_bytes,
+           "d2h_bytes_per_step": 2 * nf * field_bytes, "ms_per_step": e2e_ms,
+           "api": "mlegs_b200_trans_host (host s%e in, host s%e out), pinned host arrays"}
+
+    # ---- CPU baseline on rank 0: bounded sample of the same workload with the oracle port ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        nthreads = min(os.cpu_count() or 1, 16)
+        rate, t = cpu_roundtrip_rate(kit.tables(), oracle_params(p), nthreads, nthreads, reps=2)
+        cpu = {"value": rate * dof / 1e9, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": f"{nthreads} fields x 1 round trip (best of 2), NumPy oracle port of ops:157-235, "
+                         "one field per thread"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"PPP<->FFF round trip {args.size}^3 (BASELINE.json configs[1])",
+                           "fields_per_step_per_gpu": nf, "l2_policy": f"inputs larger than L2: {nf} distinct fields "
+                           f"x {field_bytes / 1e6:.1f} MB per GPU", "parallelism": f"independent scalars x{world}",
+                           **{k: (float(v) if isinstance(v, float) else v) for k, v in wl.items()}},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--fields", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

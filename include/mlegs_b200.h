@@ -66,6 +66,11 @@ int mlegs_b200_device_sync(void);
 /* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
 long long mlegs_b200_launch_count(int reset);
 
+/* per-kernel CUDA-event timing on the launching stream; report is a JSON object
+ * {"kernel": {"launches": n, "ms": total}, ...} and clears the records */
+int mlegs_b200_prof_enable(int on);
+int mlegs_b200_prof_report(char *buf, size_t nbuf);
+
 /* ---- transform kit: host tables (tfm%init(), sinit:6-154) ---------------------------- */
 /* sizes: x,w,ln,r: nr;  lognorm: (nrchop+14)*npchop;  pf: (nr/2)*(nrchop+14)*npchop;
  * at0,at1: nrchop;  ak: nz.  All column-major like the Fortran arrays.  Host code, runs the

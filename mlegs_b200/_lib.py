@@ -47,6 +47,8 @@ _SIGS = {
     "mlegs_b200_set_stream": (C.c_int, [C.c_void_p]),
     "mlegs_b200_device_sync": (C.c_int, []),
     "mlegs_b200_launch_count": (C.c_longlong, [C.c_int]),
+    "mlegs_b200_prof_enable": (C.c_int, [C.c_int]),
+    "mlegs_b200_prof_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "mlegs_b200_tfm_tables": (C.c_int, [_P(Params)] + [C.c_void_p] * 9),
     "mlegs_b200_init": (C.c_int, [_P(Params)] + [C.c_void_p] * 6 + [C.c_int, C.c_int]),
     "mlegs_b200_finalize": (C.c_int, []),

@@ -263,6 +263,8 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
   for (int i = 0; i < FFT_MAXPASS; ++i) pl.radix[i] = plan.radix[i];
   dim3 grid((unsigned)((batch0 + plan.ti - 1) / plan.ti), (unsigned)batch1);
   const cplx *twc = reinterpret_cast<const cplx *>(tw);
+  static const char *names[4] = {"fft_z_forward", "fft_z_backward", "fft_phi_forward", "fft_phi_backward"};
+  prof_begin(names[(int)mode], st);
   switch (mode) {
     case FFT_C2C_FWD:
       fft_lines_kernel<FFT_C2C_FWD><<<grid, FFT_THREADS, plan.smem, st>>>(in, out, plan.n, plan.ti, batch0, stride_pt,
@@ -281,6 +283,7 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
                                                                           stride_b1, twc, tw_order, scale, pl);
       break;
   }
+  prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
 }

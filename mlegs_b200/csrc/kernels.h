@@ -8,6 +8,10 @@ namespace mlegs {
 
 typedef double2 cplx;
 
+// prof.cu: optional CUDA-event timing around each launch
+void prof_begin(const char *name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
 // ---- fft.cu ----------------------------------------------------------------------------
 int make_fft_plan(int n_complex, int extra_points, FftPlan *plan);
 int setup_fft_kernels();

@@ -308,7 +308,9 @@ int setup_leg_kernels() {
 int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrdim + LEG_MT_F - 1) / LEG_MT_F, a.npl);
+  prof_begin("legendre_forward", st);
   leg_forward_kernel<<<grid, LEG_THREADS, 2 * sizeof(FwdSmem), st>>>(a);
+  prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
 }
@@ -316,7 +318,9 @@ int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
 int launch_leg_backward(const LegArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrh + LEG_MT_B - 1) / LEG_MT_B, a.npl);
+  prof_begin("legendre_backward", st);
   leg_backward_kernel<<<grid, LEG_THREADS, 2 * sizeof(BwdSmem), st>>>(a);
+  prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
 }

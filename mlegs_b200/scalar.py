@@ -180,3 +180,13 @@ def is_finite(s) -> bool:
 def device_sync(): check(_l().mlegs_b200_device_sync())
 def set_stream(ptr): check(_l().mlegs_b200_set_stream(C.c_void_p(ptr)))
 def launch_count(reset=False) -> int: return int(_l().mlegs_b200_launch_count(int(reset)))
+
+
+def prof_enable(on: bool = True): check(_l().mlegs_b200_prof_enable(int(on)))
+
+
+def prof_report() -> dict:
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(_l().mlegs_b200_prof_report(buf, len(buf)))
+    return json.loads(buf.value.decode())
