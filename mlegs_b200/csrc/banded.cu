@@ -1,0 +1,490 @@
+// Spectral differential operators (banded mat-vec) and the semi-implicit solves (row-pivoted banded LU),
+// one (m,k) column per CTA / warp.  Reference: /root/reference/src/submodules/mlegs_scalar_ops.f90:418-1000
+// with the coefficient formulas of mlegs_spectfm_diff.f90:6-152 and LAPACK's zgbtf2/zgbtrs/ztbsv
+// operation order (external/lapack/SRC/zgbtf2.f:219-262, zgbtrs.f:205-232).
+//
+// The reference rebuilds a dense nn x nn matrix with nn^2 exp() calls for every (m,k); here the
+// lognorm-scaled band coefficients are tabulated once per m on the host (same formulas, same libm) and
+// the -k^2 shift is applied on the fly.  Compiled with -fmad=false: products and sums round separately,
+// in the reference's order, so matrices are bit-identical to a non-fused CPU evaluation.
+#include <cmath>
+#include <thread>
+
+#include "kernels.h"
+
+namespace mlegs {
+
+// ---------------------------------------------------------------------------------------------
+// host tables: leg_xxdx (sdiff:6-43) and leg_del2h (sdiff:45-96) for the untruncated band
+// ---------------------------------------------------------------------------------------------
+int build_operator_tables() {
+  Context &c = ctx();
+  const int ne = c.ne, nm = c.p.npchop;
+  const double ell2 = std::pow(c.p.ell, 2.0);
+  c.h_del2h.assign((size_t)nm * 5 * ne, 0.0);
+  c.h_xxdx.assign((size_t)nm * 3 * ne, 0.0);
+  const double s = 0.0;
+  for (int am = 0; am < nm; ++am) {
+    const double *ln = c.h_lognorm.data() + (size_t)am * ne;
+    double *t5 = c.h_del2h.data() + (size_t)am * 5 * ne;
+    double *t3 = c.h_xxdx.data() + (size_t)am * 3 * ne;
+    for (int i = 0; i < ne; ++i) {
+      const double n = (double)(am + i);
+      const double nam = (double)(i);   // n - am
+      double v[5];
+      v[0] = -(n - am - 1.0) * nam * (n - 2.0 + s) * (n - 1.0 + s) / (2.0 * n - 3.0) / (2.0 * n - 1.0);
+      v[1] = 2.0 * n * nam * (n - 1.0 + s) / (2.0 * n - 1.0);
+      v[2] = (-2.0 * n * (n + 1.0) * (3.0 * n * n + 3.0 * n - (double)(am * am) - 2.0) +
+              2.0 * s * (s - 2.0) * (n * n + n + (double)(am * am) - 1.0)) /
+             (2.0 * n - 1.0) / (2.0 * n + 3.0);
+      v[3] = 2.0 * (n + 1.0) * (n + am + 1.0) * (n + 2.0 - s) / (2.0 * n + 3.0);
+      v[4] = -(n + am + 1.0) * (n + am + 2.0) * (n + 3.0 - s) * (n + 2.0 - s) / (2.0 * n + 3.0) / (2.0 * n + 5.0);
+      for (int b = 0; b < 5; ++b) {
+        int j = i + b - 2;
+        if (j < 0 || j >= ne) continue;
+        double g = v[b] / ell2;
+        t5[(size_t)b * ne + i] = g * std::exp(ln[j] - ln[i]);
+      }
+      double x[3];
+      x[0] = -(n - 1.0) * nam / (2.0 * n - 1.0);
+      x[1] = 0.0;
+      x[2] = (n + 2.0) * (n + am + 1.0) / (2.0 * n + 3.0);
+      for (int b = 0; b < 3; ++b) {
+        int j = i + b - 1;
+        if (j < 0 || j >= ne || b == 1) continue;
+        t3[(size_t)b * ne + i] = x[b] * std::exp(ln[j] - ln[i]);
+      }
+    }
+  }
+  CUDA_TRY(cudaMalloc((void **)&c.d_del2h, c.h_del2h.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(c.d_del2h, c.h_del2h.data(), c.h_del2h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc((void **)&c.d_xxdx, c.h_xxdx.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(c.d_xxdx, c.h_xxdx.data(), c.h_xxdx.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc((void **)&c.d_flag, 4 * sizeof(int)));
+  CUDA_TRY(cudaMemset(c.d_flag, 0, 4 * sizeof(int)));
+
+  // vec2tp projection tables (ops:1405-1410): v = pf/n/(n+1)/fff, d = (pf .mul. xxdx)/n/(n+1)/fff
+  const int nrh = c.nrh, nr = c.p.nr;
+  std::vector<double> hv((size_t)nrh * ne * nm, 0.0), hd((size_t)nrh * ne * nm, 0.0);
+  std::vector<double> hpf((size_t)nrh * ne * nm);
+  CUDA_TRY(cudaMemcpy(hpf.data(), c.d_pf, hpf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<double> fff(nrh);
+  for (int i = 0; i < nrh; ++i) fff[i] = (1.0 - std::pow(c.h_x[i], 2.0)) / c.h_w[i];
+  (void)nr;
+  unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nthreads; ++t) {
+    pool.emplace_back([&, t]() {
+      for (int m = (int)t; m < nm; m += (int)nthreads) {
+        const double *pf = hpf.data() + (size_t)m * nrh * ne;
+        const double *t3 = c.h_xxdx.data() + (size_t)m * 3 * ne;
+        double *v = hv.data() + (size_t)m * nrh * ne;
+        double *d = hd.data() + (size_t)m * nrh * ne;
+        for (int col = 0; col + 1 < ne; ++col) {
+          int nq = std::max(1, m + col);
+          for (int i = 0; i < nrh; ++i) {
+            // pfd(:,col) = sum_k pf(:,k) X(k,col), k ascending (bops:135-160); X(k,col) = t3[(col-k+1)][k]
+            double acc = 0.0;
+            if (col - 1 >= 0) acc = acc + pf[(size_t)(col - 1) * nrh + i] * t3[(size_t)2 * ne + (col - 1)];
+            acc = acc + pf[(size_t)col * nrh + i] * 0.0;
+            acc = acc + pf[(size_t)(col + 1) * nrh + i] * t3[(size_t)0 * ne + (col + 1)];
+            v[(size_t)col * nrh + i] = pf[(size_t)col * nrh + i] / nq / (nq + 1) / fff[i];
+            d[(size_t)col * nrh + i] = acc / nq / (nq + 1) / fff[i];
+          }
+        }
+      }
+    });
+  }
+  for (auto &th : pool) th.join();
+  CUDA_TRY(cudaMalloc((void **)&c.d_vtab, hv.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(c.d_vtab, hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc((void **)&c.d_dtab, hd.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(c.d_dtab, hd.data(), hd.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return MLEGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// banded mat-vec: xxdx / del2h / del2 / helmp
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nn_of(int mglob, int nrc, int npc) {
+  if (mglob >= npc) return 0;
+  int v = min(nrc, nrc - mglob);
+  return v > 0 ? v : 0;
+}
+
+// how many times the reference's two axial loops visit plane k (0-based); see k_ranges in the oracle
+__device__ __forceinline__ int k_visits(int k, int nzl, int nzc, int nzcu) {
+  int v = 0;
+  if (k < min(nzl, nzc)) v++;
+  int lo = max(nzcu, 1) - 1;
+  if (k >= lo && k < nzl) v++;
+  return v;
+}
+
+__global__ void band_op_kernel(BandOpArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx *s0 = reinterpret_cast<cplx *>(smraw);
+  cplx *b1 = s0 + a.nrl, *b2 = b1 + a.nrl, *s2 = b2 + a.nrl;
+  const int j = blockIdx.x, k = blockIdx.y;
+  const int mglob = a.m0 + j;
+  const int nn = nn_of(mglob, a.nrc, a.npc);
+  const int reps = (nn >= 1) ? k_visits(k, a.nzl, a.nzc, a.nzcu) : 0;
+  const bool lncol = (mglob == 0 && k == 0 && a.nlnc > 0);
+  if (!a.combine && reps == 0 && !lncol) return;
+  cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+  const double *tab = a.tab + (size_t)mglob * a.nb * a.ne;
+  const int half = a.nb / 2;
+  double ak2 = 0.0;
+  if (a.ak) {
+    double akv = a.ak[k];
+    ak2 = akv * akv;
+  }
+  for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
+    cplx v = col[i];
+    s0[i] = v;
+    b1[i] = v;
+  }
+  __syncthreads();
+  cplx *cur = b1, *nxt = b2;
+  for (int ap = 0; ap < a.napply; ++ap) {
+    for (int r = 0; r < reps; ++r) {
+      for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
+        cplx o = cur[i];
+        if (i < nn) {
+          double ar = 0.0, ai = 0.0;
+          for (int b = 0; b < a.nb; ++b) {
+            int jj = i + b - half;
+            if (jj < 0 || jj >= nn) continue;
+            double cf = tab[(size_t)b * a.ne + i];
+            if (b == half && a.ak) cf = cf - ak2;
+            cplx x = cur[jj];
+            ar = ar + x.x * cf;
+            ai = ai + x.y * cf;
+          }
+          o = make_double2(ar, ai);
+        }
+        nxt[i] = o;
+      }
+      __syncthreads();
+      cplx *t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    if (ap == 0) {
+      if (lncol) {
+        if (threadIdx.x < a.nlnc) cur[threadIdx.x].x = cur[threadIdx.x].x + a.lnc[threadIdx.x];
+        __syncthreads();
+      }
+      if (a.combine) {
+        for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) s2[i] = cur[i];
+        __syncthreads();
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
+    cplx o = cur[i];
+    if (a.combine) {
+      cplx q = s2[i], s = s0[i];
+      o = make_double2((o.x + a.beta * q.x) + a.alpha * s.x, (o.y + a.beta * q.y) + a.alpha * s.y);
+    }
+    col[i] = o;
+  }
+}
+
+int launch_band_op(const BandOpArgs &a, cudaStream_t st) {
+  if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
+  size_t smem = (size_t)4 * a.nrl * sizeof(cplx);
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && smem > attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(band_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  dim3 grid(a.npl, a.nzl);
+  int threads = a.nrl >= 256 ? 256 : 128;
+  prof_begin(a.combine ? "helmp_band" : (a.nb == 3 ? "xxdx_band" : "del2_band"), st);
+  band_op_kernel<<<grid, threads, smem, st>>>(a);
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// banded solves: ihelm / idel2 / ihelmp.  One warp per (m,k) system.
+// workspace per system (doubles): D[5 nn] | Pa[17 nn] | AB[ldab nn] (aliases Pb) | rhs[2 nn]
+// ---------------------------------------------------------------------------------------------
+#define SOLVE_WARPS 4
+
+__device__ __forceinline__ void warp_argmax_first(double &v, int &idx) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, off);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (ov > v || (ov == v && oi < idx)) {
+      v = ov;
+      idx = oi;
+    }
+  }
+}
+
+// P_out = D * P_in for nn x nn band matrices; P has half-width hw_in (bands -hw_in..hw_in, stored [(dc+HW)*nn + r]).
+__device__ void band_product(const double *D, const double *Pin, int pin_off, double *Pout, int nn, int hw_in,
+                             int HW, int lane) {
+  const int hw_out = hw_in + 2;
+  const int total = (2 * hw_out + 1) * nn;
+  for (int idx = lane; idx < total; idx += 32) {
+    int dc = idx / nn - hw_out;
+    int r = idx - (dc + hw_out) * nn;
+    int jc = r + dc;
+    double acc = 0.0;
+    if (jc >= 0 && jc < nn) {
+      for (int da = -2; da <= 2; ++da) {
+        int kk = r + da;
+        int db = dc - da;
+        if (kk < 0 || kk >= nn || db < -hw_in || db > hw_in) continue;
+        acc = acc + D[(da + 2) * nn + r] * Pin[(db + pin_off) * nn + kk];
+      }
+    }
+    Pout[(dc + HW) * nn + r] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nsys = a.npl * a.nk;
+  const int kl = a.kl, ku = a.ku, kv = kl + ku, ldab = 2 * kl + ku + 1;
+  const int HW = 8;
+  for (int sys = blockIdx.x * SOLVE_WARPS + warp; sys < nsys; sys += gridDim.x * SOLVE_WARPS) {
+    const int j = sys % a.npl;
+    const int k = a.k0 + sys / a.npl;
+    const int mglob = a.m0 + j;
+    const int nn = nn_of(mglob, a.nrc, a.npc);
+    if (nn < 1) continue;
+    double *ws = a.ws_global ? a.ws_global + (size_t)(blockIdx.x * SOLVE_WARPS + warp) * a.ws_doubles
+                             : reinterpret_cast<double *>(smraw) + (size_t)warp * a.ws_doubles;
+    double *D = ws;
+    double *Pa = D + 5 * a.nnmax;
+    double *AB = Pa + (a.power > 2 ? 17 * a.nnmax : 0);
+    double *Pb = AB;
+    double *rhs = AB + (size_t)ldab * a.nnmax;
+    cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+    const double *tab = a.tab + (size_t)mglob * 5 * a.ne;
+    const double akv = a.ak[k];
+    const double ak2 = akv * akv;
+    const bool special = (a.special00 && mglob == 0 && k == 0);
+
+    // ---- D = leg_del2(m, ak(k), nn, nn) ----
+    for (int idx = lane; idx < 5 * nn; idx += 32) {
+      int b = idx / nn, r = idx - b * nn;
+      int jc = r + b - 2;
+      double cf = 0.0;
+      if (jc >= 0 && jc < nn) {
+        cf = tab[(size_t)b * a.ne + r];
+        if (b == 2) cf = cf - ak2;
+      }
+      D[b * nn + r] = cf;
+    }
+    for (int idx = lane; idx < ldab * nn; idx += 32) AB[idx] = 0.0;
+    // rhs (shifted down by one row for the prescribed-ln variant, ops:621-622)
+    for (int i = lane; i < nn; i += 32) {
+      cplx v;
+      if (special && a.special00 == 2)
+        v = (i == 0) ? make_double2(a.preln_rhs, 0.0) : col[i - 1];
+      else
+        v = col[i];
+      rhs[2 * i] = v.x;
+      rhs[2 * i + 1] = v.y;
+    }
+    __syncwarp();
+
+    // ---- operator matrix into LAPACK band storage AB(kv + i - j, j) ----
+    const double *H = D;
+    int hwH = 2, HWs = 2;   // H stored with offset HWs
+    if (a.power > 2) {
+      // helmp_bnd = del2 .mul. helmp_bnd, power/2-1 times (ops:958-962).  Pb aliases AB, so the buffers
+      // alternate such that the last product lands in Pa.
+      int nprod = a.power / 2 - 1;
+      const double *src = D;
+      int hw = 2, src_off = 2;
+      double *dst = (nprod % 2 == 1) ? Pa : Pb;
+      for (int q = 0; q < nprod; ++q) {
+        band_product(D, src, src_off, dst, nn, hw, HW, lane);
+        __syncwarp();
+        src = dst;
+        src_off = HW;
+        hw += 2;
+        dst = (dst == Pa) ? Pb : Pa;
+      }
+      H = src;   // == Pa
+      hwH = hw;
+      HWs = HW;
+      __syncwarp();
+      // AB aliases Pb, which is dead now
+      for (int idx = lane; idx < ldab * nn; idx += 32) AB[idx] = 0.0;
+      __syncwarp();
+    }
+    {
+      const int nbands = 2 * hwH + 1;
+      for (int idx = lane; idx < nbands * nn; idx += 32) {
+        int dc = idx / nn - hwH;
+        int r = idx - (dc + hwH) * nn;
+        int jc = r + dc;
+        if (jc < 0 || jc >= nn) continue;
+        if (dc > ku || -dc > kl) continue;
+        double v = H[(dc + HWs) * nn + r];
+        if (a.power > 2) {
+          double dv = (dc >= -2 && dc <= 2) ? D[(dc + 2) * nn + r] : 0.0;
+          v = v + a.beta * dv;           // fullmat(helmp) + beta*fullmat(del2), ops:963
+        }
+        if (dc == 0 && a.add_alpha) v = v + a.alpha;
+        AB[(kv - dc) + (size_t)jc * ldab] = v;
+      }
+      __syncwarp();
+    }
+    if (special && lane == 0) {
+      if (a.special00 == 1) {
+        // idel2_proln, ops:705-711: first column picks up the log-term's Laplacian
+        AB[(kv + 0) + 0 * ldab] = AB[(kv + 0)] + a.sp0;
+        AB[(kv + 1) + 0 * ldab] = AB[(kv + 1)] - a.sp1;
+        AB[(kv + 2) + 0 * ldab] = AB[(kv + 2)] + a.sp2;
+      }
+    }
+    if (special && a.special00 == 2) {
+      // idel2_preln, ops:609-618: rows shifted down by one, first row = e_1^T, first column corrected
+      __syncwarp();
+      for (int idx = lane; idx < ldab * nn; idx += 32) AB[idx] = 0.0;
+      __syncwarp();
+      for (int idx = lane; idx < 5 * nn; idx += 32) {
+        int b = idx / nn, r = idx - b * nn;     // D(r, r+b-2) moves to row r+1
+        int jc = r + b - 2, ir = r + 1;
+        if (jc < 0 || jc >= nn || ir >= nn) continue;
+        AB[(kv + ir - jc) + (size_t)jc * ldab] = D[b * nn + r];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        AB[kv + 0] = 1.0;
+        AB[kv + 1] = AB[kv + 1] + a.sp0;
+        if (nn > 2) AB[kv + 2] = AB[kv + 2] - a.sp1;
+        if (nn > 3) AB[kv + 3] = AB[kv + 3] + a.sp2;
+      }
+    }
+    __syncwarp();
+
+    // ---- zgbtf2 with the forward substitution of zgbtrs applied on the fly ----
+    int ju = 0;
+    for (int jj = 0; jj < nn; ++jj) {
+      const int km = min(kl, nn - 1 - jj);
+      double *cj = AB + (size_t)jj * ldab;
+      double pv = (lane <= km) ? fabs(cj[kv + lane]) : -1.0;
+      int jp = lane;
+      warp_argmax_first(pv, jp);
+      if (pv != 0.0) {
+        ju = max(ju, min(jj + ku + jp, nn - 1));
+        const int ncol = ju - jj + 1;
+        if (jp != 0) {
+          for (int cc = lane; cc < ncol; cc += 32) {
+            double *p1 = AB + (size_t)(jj + cc) * ldab + (kv + jp - cc);
+            double *p2 = AB + (size_t)(jj + cc) * ldab + (kv - cc);
+            double t = *p1;
+            *p1 = *p2;
+            *p2 = t;
+          }
+          if (lane == 0) {
+            double tr = rhs[2 * (jj + jp)], ti = rhs[2 * (jj + jp) + 1];
+            rhs[2 * (jj + jp)] = rhs[2 * jj];
+            rhs[2 * (jj + jp) + 1] = rhs[2 * jj + 1];
+            rhs[2 * jj] = tr;
+            rhs[2 * jj + 1] = ti;
+          }
+          __syncwarp();
+        }
+        if (km > 0) {
+          const double rinv = 1.0 / cj[kv];
+          __syncwarp();
+          if (lane >= 1 && lane <= km) cj[kv + lane] = cj[kv + lane] * rinv;
+          __syncwarp();
+          const int nupd = km * (ncol - 1);
+          for (int idx = lane; idx < nupd; idx += 32) {
+            int r = 1 + idx % km, cc = 1 + idx / km;
+            double *col2 = AB + (size_t)(jj + cc) * ldab;
+            double temp = -col2[kv - cc];
+            col2[kv + r - cc] = col2[kv + r - cc] + cj[kv + r] * temp;
+          }
+          if (lane >= 1 && lane <= km) {
+            double l = cj[kv + lane];
+            double tr = -rhs[2 * jj], ti = -rhs[2 * jj + 1];
+            rhs[2 * (jj + lane)] = rhs[2 * (jj + lane)] + l * tr;
+            rhs[2 * (jj + lane) + 1] = rhs[2 * (jj + lane) + 1] + l * ti;
+          }
+          __syncwarp();
+        }
+      } else if (lane == 0) {
+        atomicOr(a.flag + 1, 1);   // 'lurc: lu factorization resulted in failure'
+      }
+    }
+    // ---- ztbsv: upper, no transpose, non-unit, bandwidth kv ----
+    for (int jj = nn - 1; jj >= 0; --jj) {
+      const double *cj = AB + (size_t)jj * ldab;
+      double xr = rhs[2 * jj], xi = rhs[2 * jj + 1];
+      if (xr != 0.0 || xi != 0.0) {
+        const double ujj = cj[kv];
+        xr = xr / ujj;
+        xi = xi / ujj;
+        __syncwarp();
+        if (lane == 0) {
+          rhs[2 * jj] = xr;
+          rhs[2 * jj + 1] = xi;
+        }
+        const int cnt = min(jj, kv);
+        if (lane >= 1 && lane <= cnt) {
+          int i = jj - lane;
+          double u = cj[kv - lane];
+          rhs[2 * i] = rhs[2 * i] - xr * u;
+          rhs[2 * i + 1] = rhs[2 * i + 1] - xi * u;
+        }
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < nn; i += 32) col[i] = make_double2(rhs[2 * i], rhs[2 * i + 1]);
+    __syncwarp();
+  }
+}
+
+int launch_band_solve(SolveArgs a, cudaStream_t st) {
+  Context &c = ctx();
+  if (a.npl <= 0 || a.nk <= 0) return MLEGS_OK;
+  const int ldab = 2 * a.kl + a.ku + 1;
+  a.ws_doubles = (size_t)(5 + (a.power > 2 ? 17 : 0) + ldab + 2) * a.nnmax;
+  // Pb (used from power 6 on) aliases AB and holds at most 13 bands stored with offset 8 -> 15 nn doubles
+  if (a.power > 4 && ldab < 15) return fail(MLEGS_E_ARG, "band_solve: internal workspace aliasing violated");
+  size_t smem = a.ws_doubles * sizeof(double) * SOLVE_WARPS;
+  const int nsys = a.npl * a.nk;
+  int blocks = (nsys + SOLVE_WARPS - 1) / SOLVE_WARPS;
+  a.flag = c.d_flag;
+  if (smem <= 200 * 1024) {
+    a.ws_global = nullptr;
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(band_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = smem;
+    }
+  } else {
+    // large systems: per-warp workspace in global memory (L2 resident), persistent grid
+    smem = 0;
+    blocks = std::min(blocks, 148 * 8);
+    size_t need = (size_t)blocks * SOLVE_WARPS * a.ws_doubles * sizeof(double);
+    if (need > c.solve_ws_bytes) {
+      if (c.d_solve_ws) CUDA_TRY(cudaFree(c.d_solve_ws));
+      CUDA_TRY(cudaMalloc(&c.d_solve_ws, need));
+      c.solve_ws_bytes = need;
+    }
+    a.ws_global = (double *)c.d_solve_ws;
+  }
+  prof_begin(a.power > 2 ? "ihelmp_solve" : "band_solve", st);
+  band_solve_kernel<<<blocks, SOLVE_WARPS * 32, smem, st>>>(a);
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+}  // namespace mlegs

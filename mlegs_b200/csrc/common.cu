@@ -97,7 +97,8 @@ static int free_all() {
   Context &c = ctx();
   void *ptrs[] = {c.d_x, c.d_w, c.d_lnx, c.d_r, c.d_lognorm, c.d_pf, c.d_at0, c.d_at1, c.d_ak, c.d_tw_p,
                   c.d_tw_z, c.d_del2h, c.d_xxdx, c.d_vtab, c.d_dtab, c.d_scratch[0], c.d_scratch[1],
-                  c.d_scratch[2], c.d_red, c.d_solve_ws, c.d_flags};
+                  c.d_scratch[2], c.d_scratch[3], c.d_scratch[4], c.d_scratch[5], c.d_red, c.d_solve_ws, c.d_flags,
+                  c.d_flag};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (c.h_red) cudaFreeHost(c.h_red);
@@ -235,9 +236,9 @@ int mlegs_b200_init(const mlegs_params *p, const double *x, const double *w, con
   size_t n_ppp = (size_t)c.r_cnt[0] * c.npdim * c.nzdim;
   size_t n_fff = (size_t)c.nrdim * c.m_cnt[0] * c.nzdim;
   c.field_bytes = std::max(n_ppp, n_fff) * sizeof(cplx);
-  for (int i = 0; i < 3; ++i) CUDA_TRY(cudaMalloc(&c.d_scratch[i], c.field_bytes));
-  CUDA_TRY(cudaMalloc((void **)&c.d_red, 4096 * sizeof(double)));
-  CUDA_TRY(cudaMallocHost((void **)&c.h_red, 4096 * sizeof(double)));
+  for (int i = 0; i < 6; ++i) CUDA_TRY(cudaMalloc(&c.d_scratch[i], c.field_bytes));
+  CUDA_TRY(cudaMalloc((void **)&c.d_red, Context::RED_DOUBLES * sizeof(double)));
+  CUDA_TRY(cudaMallocHost((void **)&c.h_red, Context::RED_DOUBLES * sizeof(double)));
   c.ready = true;
   MLEGS_TRY(build_operator_tables());
   return MLEGS_OK;

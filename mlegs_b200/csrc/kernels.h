@@ -26,8 +26,8 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
 struct LegArgs {
   const cplx *in;
   cplx *out;
-  const double *pf;      // (nrh, ne, npchop)
-  const double *w;       // nr
+  const double *pf;      // (nrh, ne, npchop) table contracted against (pf, or the v/d projection tables)
+  const double *w;       // nr quadrature weights (forward only; nullptr: no weighting)
   const double *lnx;     // nr, -log(1-x)
   int nr, nrh, ne;
   int nrl;               // leading dimension (rows) of in/out == nrdim
@@ -37,9 +37,114 @@ struct LegArgs {
   int nrc, npc;          // chop limits incl. offsets: nn(m) = max(min(nrc, nrc-m),0) for m < npc
   int nrdim;
   double lnval;          // s%ln (log-term), applied on global m == 0
+  int swap_parity;       // forward only: 0 = eomul (even rows <- even fold), 1 = oemul (ops:2067-2145)
+  int skip_m0;           // forward only: leave the m == 0 column zero (vec2tp: `if (mv .ne. 0)`)
 };
 int setup_leg_kernels();
 int launch_leg_forward(const LegArgs &a, cudaStream_t st);
 int launch_leg_backward(const LegArgs &a, cudaStream_t st);
+
+// ---- elementwise.cu ---------------------------------------------------------------------
+struct MaskArgs {
+  cplx *e;
+  int nrl, npl, nzl, r0, m0;
+  int row_mode;
+  int nrc, npc_rows;
+  int col_cut;
+  int kz_lo, kz_hi;
+};
+int launch_mask(const MaskArgs &a, cudaStream_t st);
+
+struct SvvArgs {
+  cplx *e;
+  int nrl, npl, nzl, r0, m0;
+  const double *ak;
+  int nak;
+  double qr_den, qp_den, kmax, cutoff, strength;
+};
+int launch_svv_energy(const SvvArgs &a, double *d_partial, double *d_out2, cudaStream_t st);
+int launch_svv_apply(const SvvArgs &a, cudaStream_t st);
+
+int launch_calcat(cplx *e, int nrl, int npl, int nzl, int nrows, const double *at, cplx *out, int subtract,
+                  double at_first, cudaStream_t st);
+int launch_delsqp(cplx *e, int nrl, int npl, int nzl, int m0, int nrc, int npc, double ell2, int inverse,
+                  cudaStream_t st);
+struct PokeArgs {
+  int n;
+  long long off[4];
+  double re[4], im[4];
+  int mode[4];   // 0: set, 1: add
+};
+int launch_poke(cplx *e, const PokeArgs &p, cudaStream_t st);
+int launch_zero_line(cplx *e, long long off, long long stride, int n, cudaStream_t st);
+int launch_vecprod(cplx *vr, cplx *vp, cplx *vz, const cplx *ur, const cplx *up, const cplx *uz, int nrl, int npl,
+                   int nzl, int r0, int nr, int nph, int nz, cudaStream_t st);
+struct LinArgs {
+  int mode;
+  size_t n;
+  cplx *y;
+  const cplx *x1, *x2, *x3;
+  double a, b, c;
+};
+int launch_lincomb(const LinArgs &p, cudaStream_t st);
+int launch_rscale(cplx *e, int nrl, size_t ncols, int r0, int nr, const double *r, int divide, cudaStream_t st);
+int launch_finite(const cplx *e, size_t n, int *flag, cudaStream_t st);
+int launch_col_update(cplx *col, int n, int mode, const double *v1, const double *v2, double s, cudaStream_t st);
+
+// vec2tp combination (ops:1413-1435) and tp2vec combination (ops:1488-1502)
+struct TpCombineArgs {
+  cplx *dst;                             // psi or chi, rows < nn of the retained (m,k) columns only
+  const cplx *t;                         // one of eomul(v,ur), oemul(d,up), oemul(d,ur), eomul(v,up), eomul(t,uz)
+  int mode;                              // 0: dst=(-iu*mv)*t  1: dst-=t  2: dst=(iu*kv)*t  3: dst+=(mv*kv)*t  4: dst-=t
+  int nrl, npl, nzl, m0;
+  int nrc, npc, nzc, nzcu;
+  const double *ak;
+};
+int launch_tp_combine(const TpCombineArgs &a, cudaStream_t st);
+struct TvCombineArgs {
+  cplx *ur, *up;                         // in: xxdx(chi), xxdx(psi); out: combined
+  const cplx *psi, *uz;                  // psi, chi
+  int nrl, npl, nzl, m0;
+  int nrc, npc, nzc, nzcu;
+  const double *ak;
+};
+int launch_tv_combine(const TvCombineArgs &a, cudaStream_t st);
+
+// ---- banded.cu --------------------------------------------------------------------------
+struct BandOpArgs {
+  cplx *e;
+  int nrl, npl, nzl, m0;
+  const double *tab;     // (ne, nb, npchop) band coefficients
+  int nb, ne;
+  const double *ak;      // nullptr: no -ak^2 on the diagonal (xxdx, del2h)
+  int nrc, npc, nzc, nzcu;
+  int napply;            // 1, or power/2 for helmp
+  int combine;           // helmp: out = (sp + beta*s2) + alpha*s on the WHOLE array (ops:893)
+  double alpha, beta;
+  int nlnc;              // log-term corrections added to rows 0..nlnc-1 of column (m=0,k=0)
+  double lnc[3];
+};
+int launch_band_op(const BandOpArgs &a, cudaStream_t st);
+
+struct SolveArgs {
+  cplx *e;
+  int nrl, npl, m0;
+  int k0, nk;            // axial planes k0 .. k0+nk-1
+  const double *tab;     // del2h table
+  int ne;
+  const double *ak;
+  int nrc, npc;
+  int nnmax;
+  int kl, ku;
+  int power;             // 2: del2 (+alpha); 4,6,8: del^p + beta del2 + alpha
+  int add_alpha;
+  double alpha, beta;
+  int special00;         // 0 none; 1 idel2_proln column fix (ops:705-711); 2 idel2_preln (ops:609-622)
+  double sp0, sp1, sp2, preln_rhs;
+  size_t ws_doubles;
+  double *ws_global;
+  int *flag;
+};
+int launch_band_solve(SolveArgs a, cudaStream_t st);
 
 }  // namespace mlegs

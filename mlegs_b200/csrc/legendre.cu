@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   const int par = warp >> 2, wr = (warp >> 1) & 1, wc = warp & 1;
   const int ml = blockIdx.z;
   const int mglob = a.m0 + ml;
-  const int nn = nn_of_m(mglob, a.nrc, a.npc);
+  const int nn = (a.skip_m0 && mglob == 0) ? 0 : nn_of_m(mglob, a.nrc, a.npc);
   const int n0 = blockIdx.y * LEG_MT_F;
   const int kz0 = blockIdx.x * LEG_NTC;
   const size_t col_stride = (size_t)a.nrl * a.npl;     // elements between z planes
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
       int n = n0 + lr + 16 * j;
       ra[j] = (kok && n < nn) ? __ldg(&pf[(size_t)n * a.nrh + kk]) : 0.0;
     }
-    double wi = kok ? __ldg(&a.w[kk]) : 0.0;
+    double wi = kok ? (a.w ? __ldg(&a.w[kk]) : 1.0) : 0.0;
     double l1 = 0.0, l2 = 0.0;
     if (use_ln && kok) {
       l1 = a.lnval * __ldg(&a.lnx[kk]);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) af[mt] = sm[buf].A[par][wr * 32 + mt * 8 + fr][ks * 4 + fk];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bf[nt] = sm[buf].B[par][wc * 32 + nt * 8 + fr][ks * 4 + fk];
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = sm[buf].B[par ^ a.swap_parity][wc * 32 + nt * 8 + fr][ks * 4 + fk];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll

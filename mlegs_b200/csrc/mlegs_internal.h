@@ -64,6 +64,8 @@ struct Context {
   int chopzl = 0, chopzu = 0;
   // host copies
   std::vector<double> h_x, h_w, h_ln, h_lognorm, h_at0, h_at1, h_ak;
+  std::vector<double> h_del2h, h_xxdx;   // band tables, see d_del2h / d_xxdx
+  int *d_flag = nullptr;                 // device error/finite flags [0]: non-finite, [1]: singular pivot
   // device tables
   double *d_x = nullptr, *d_w = nullptr, *d_lnx = nullptr, *d_r = nullptr;
   double *d_lognorm = nullptr;   // (ne, npchop)
@@ -77,7 +79,8 @@ struct Context {
   // projection tables for vec2tp (ops:1405-1411), same shape as pf but nrchop+3 columns used
   double *d_vtab = nullptr, *d_dtab = nullptr;
   // scratch
-  void *d_scratch[3] = {nullptr, nullptr, nullptr};   // field-sized work buffers
+  void *d_scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // field-sized work buffers
+  static const int RED_DOUBLES = 32768;
   size_t field_bytes = 0;
   double *d_red = nullptr;       // small reduction workspace
   double *h_red = nullptr;       // pinned

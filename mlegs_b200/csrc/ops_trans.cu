@@ -45,6 +45,8 @@ static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
   a->npc = npc;
   a->nrdim = c.nrdim;
   a->lnval = s->ln;
+  a->swap_parity = 0;
+  a->skip_m0 = 0;
   return MLEGS_OK;
 }
 

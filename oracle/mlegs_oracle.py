@@ -220,7 +220,7 @@ def kit_init(p: Params, tables: Optional[dict] = None) -> Kit:
         x, w = gauss_legendre(nr)
     else:
         x, w = np.asarray(tables["x"], dtype=np.float64), np.asarray(tables["w"], dtype=np.float64)
-    ln = -np.log(1.0 - x)
+    ln = np.array([-math.log(1.0 - float(v)) for v in x])      # libm log, like gfortran
     r = p.ell * np.sqrt((1.0 + x) / (1.0 - x))
     chops = np.array([max(nrchop - i, 0) for i in range(npchop)], dtype=np.int64)
     nrdim = nr + max(3, p.hyperpow)
@@ -529,6 +529,25 @@ def zeroat1(s: Scalar, kit: Kit):
 # --------------------------------------------------------------------------- #
 # banded operators.  A band matrix is a dict {d: vector}: A[i, i+d] = band[d][i]
 # --------------------------------------------------------------------------- #
+_SCALE_CACHE: dict = {}
+
+
+def _scale_factors(lognorm_col: np.ndarray, d: int) -> np.ndarray:
+    """exp(lognorm(i+d) - lognorm(i)) through libm's exp (what gfortran calls; numpy's SIMD exp can
+    differ by an ulp), cached per lognorm column and diagonal."""
+    key = (hash(lognorm_col.tobytes()), lognorm_col.size, d)
+    fac = _SCALE_CACHE.get(key)
+    if fac is None:
+        nmax = lognorm_col.size
+        fac = np.ones(nmax)
+        for i in range(nmax):
+            j = i + d
+            if 0 <= j < nmax:
+                fac[i] = math.exp(lognorm_col[j] - lognorm_col[i])
+        _SCALE_CACHE[key] = fac
+    return fac
+
+
 def _scale_band(band: dict, lognorm_col: np.ndarray, n: int) -> dict:
     """genm(i,j) *= exp(lognorm(j) - lognorm(i)); e.g. sdiff:146-150."""
     out = {}
@@ -536,10 +555,8 @@ def _scale_band(band: dict, lognorm_col: np.ndarray, n: int) -> dict:
     for d, v in band.items():
         j = i + d
         ok = (j >= 0) & (j < n)
-        fac = np.ones(n)
-        fac[ok] = np.exp(lognorm_col[j[ok]] - lognorm_col[i[ok]])
-        vv = np.where(ok, v * fac, 0.0)
-        out[d] = vv
+        fac = _scale_factors(lognorm_col, d)[:n]
+        out[d] = np.where(ok, v * fac, 0.0)
     return out
 
 

@@ -1,0 +1,291 @@
+"""GPU parity of the operators, solves, integrators and vector operations against the oracle (C ABI)."""
+import numpy as np
+import pytest
+
+import mlegs_b200 as mb
+from mlegs_b200 import vortex
+from oracle import mlegs_oracle as mo
+from helpers import oracle_kit, random_fff, random_ppp, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+# (nr, np, nz, nrchop, npchop, nzchop, ell, hyperpow, visc, hypervisc)
+CASES = {
+    "gate3d": (32, 16, 8, 32, 9, 5, 4.0, 8, 1.0e-4, 5.0e-7),     # tools/validate_tutorials.py:222-238 (Nyquist plane kept)
+    "gate2d": (32, 48, 1, 32, 25, 1, 1.0, 0, 5.0e-3, 0.0),       # input_2d.params
+    "chopped": (36, 30, 20, 30, 12, 9, 2.0, 4, 1.0e-3, 1.0e-5),  # every chop below its maximum, radix 3/5 lengths
+    "hyper6": (48, 16, 12, 44, 9, 6, 3.0, 6, 1.0e-3, 1.0e-6),
+}
+TOL = 1.0e-12
+
+
+def _setup(case, **over):
+    nr, np_, nz, nrc, npc, nzc, ell, hp, visc, hv = CASES[case]
+    kw = dict(ell=ell, zlen=2 * np.pi, visc=visc, hyperpow=hp, hypervisc=hv)
+    kw.update(over)
+    p = mb.make_params(nr, np_, nz, nrc, npc, nzc, **kw)
+    kit = mb.TfmKit.init(p)
+    return kit, oracle_kit(kit)
+
+
+def _pair(ok, e, space, ln=0.0):
+    s = mb.Scalar(space).upload(e)
+    s.ln = ln
+    return s, mo.Scalar(e=e.copy(order="F"), space=space, ln=ln)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_chop_dealias_are_exact(case):
+    kit, ok = _setup(case)
+    rng = np.random.default_rng(5)
+    e = np.asfortranarray(rng.standard_normal(ok.glb_sz) + 1j * rng.standard_normal(ok.glb_sz))
+    for space in ("FFF", "PFP", "PPP", "FFP"):
+        s, so = _pair(ok, e, space)
+        mb.chop(s)
+        mo.chop(so, ok)
+        assert np.array_equal(s.download(), so.e), (case, space, "chop")
+        s, so = _pair(ok, e, space)
+        mb.dealias(s)
+        mo.dealias(so, ok)
+        assert np.array_equal(s.download(), so.e), (case, space, "dealias")
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_svv_filter(case):
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=7, decay=1.0)
+    s, so = _pair(ok, e, "FFF")
+    g, go = 0.0, 0.0
+    for _ in range(3):
+        g = mb.svv_filter(s, g)
+        go = mo.svv_filter(so, ok, go)
+        assert abs(g - go) <= 1e-13 * max(1.0, abs(go))
+        assert rel_l2(s.download(), so.e) < 1e-14
+    assert g > 0.0
+    s.space = "PPP"
+    with pytest.raises(mb.MlegsError, match="svv_filter: scalar must be in FFF space"):
+        mb.svv_filter(s, 0.0)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_farfield_values(case):
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=8)
+    s, so = _pair(ok, e, "FFF")
+    for fn, fo in ((mb.calcat0, mo.calcat0), (mb.calcat1, mo.calcat1)):
+        got, ref = fn(s), fo(so, ok)
+        assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+    mb.zeroat1(s)
+    mo.zeroat1(so, ok)
+    assert rel_l2(s.download(), so.e) < 1e-14
+    assert np.max(np.abs(mb.calcat1(s))) < 1e-12 * np.max(np.abs(e))
+    # from physical space the reference transforms a copy first (ops:251-254)
+    ep = random_ppp(ok, seed=9)
+    s, so = _pair(ok, ep, "PPP")
+    got, ref = mb.calcat0(s), mo.calcat0(so, ok)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    assert s.space == "PPP"
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("op", ["delsqp", "idelsqp", "xxdx", "del2h", "del2"])
+def test_differential_operators(case, op):
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=11)
+    for ln in (0.0, -0.41):
+        s, so = _pair(ok, e, "FFF", ln)
+        getattr(mb, op)(s)
+        getattr(mo, op)(so, ok)
+        assert rel_l2(s.download(), so.e) < TOL, (case, op, ln)
+        assert abs(s.ln - so.ln) <= 1e-13 * max(1.0, abs(so.ln))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_operators_with_chop_offset(case):
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=12)
+    for op in ("xxdx", "del2h", "del2"):
+        s, so = _pair(ok, e, "FFF", 0.2)
+        s.chop_offset(3)
+        so.chop_offset(3)
+        getattr(mb, op)(s)
+        getattr(mo, op)(so, ok)
+        assert rel_l2(s.download(), so.e) < TOL, (case, op)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("power", [4, 6, 8])
+def test_helmp_and_ihelmp(case, power):
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=13)
+    alpha, beta = 3.0e5, -150.0
+    for ln in (0.0, 0.3):
+        s, so = _pair(ok, e, "FFF", ln)
+        mb.helmp(s, power, alpha, beta)
+        mo.helmp(so, power, alpha, beta, ok)
+        assert rel_l2(s.download(), so.e) < TOL, ("helmp", case, power, ln)
+        assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
+        s, so = _pair(ok, e, "FFF", ln)
+        mb.ihelmp(s, power, alpha, beta)
+        mo.ihelmp(so, power, alpha, beta, ok)
+        assert rel_l2(s.download(), so.e) < 1e-10, ("ihelmp", case, power, ln)
+    with pytest.raises(mb.MlegsError, match="ihelmp: alpha equals to zero"):
+        mb.ihelmp(s, power, 0.0, beta)
+    with pytest.raises(mb.MlegsError, match="helmp: even power greater than or equal to 4"):
+        mb.helmp(s, 3, alpha, beta)
+    with pytest.raises(mb.MlegsError, match="power must be less than or equal to 8"):
+        mb.ihelmp(s, 10, alpha, beta)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_ihelm_and_idel2(case):
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=14)
+    for ln in (0.0, 0.25):
+        s, so = _pair(ok, e, "FFF", ln)
+        mb.ihelm(s, -200.0)
+        mo.ihelm(so, -200.0, ok)
+        assert rel_l2(s.download(), so.e) < 1e-11, ("ihelm", case, ln)
+        assert abs(s.ln - so.ln) <= 1e-13 * max(1.0, abs(so.ln))
+    s, so = _pair(ok, e, "FFF")
+    mb.idel2(s)
+    mo.idel2_proln(so, ok)
+    assert rel_l2(s.download(), so.e) < 1e-10, ("idel2_proln", case)
+    assert abs(s.ln - so.ln) <= 1e-10 * max(1.0, abs(so.ln))
+    s, so = _pair(ok, e, "FFF")
+    mb.idel2(s, preln=0.7)
+    mo.idel2_preln(so, ok, 0.7)
+    assert rel_l2(s.download(), so.e) < 1e-10, ("idel2_preln", case)
+    assert abs(s.ln - so.ln) <= 1e-10 * max(1.0, abs(so.ln))
+    with pytest.raises(mb.MlegsError, match="ihelm: alpha equals to zero"):
+        mb.ihelm(s, 0.0)
+
+
+def test_idel2_inverts_del2():
+    # apps/inverse_laplacian.f90
+    kit, ok = _setup("gate2d")
+    e = np.zeros(ok.glb_sz, dtype=np.complex128, order="F")
+    e[1, 1, 0] = 1.0
+    e[1, 2, 0] = 1.0
+    s = mb.Scalar("FFF").upload(e)
+    mb.del2(s)
+    mb.idel2(s)
+    assert rel_l2(s.download(), e) < 1e-12
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_time_integrators(case):
+    kit, ok = _setup(case)
+    e, n1, n2 = random_fff(ok, 15), 0.1 * random_fff(ok, 16), 0.1 * random_fff(ok, 17)
+    dt = 1.0e-2
+    for name in ("fefe", "febe"):
+        s, so = _pair(ok, e, "FFF", 0.1)
+        nl, nlo = _pair(ok, n1, "FFF", -0.05)
+        getattr(mb, name)(s, nl, dt)
+        getattr(mo, name)(so, nlo, dt, ok)
+        assert rel_l2(s.download(), so.e) < 1e-10, (case, name)
+        assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
+    s, so = _pair(ok, e, "FFF", 0.1)
+    sp, spo = _pair(ok, e, "FFF", 0.1)
+    nl, nlo = _pair(ok, n1, "FFF", -0.05)
+    nlp, nlpo = _pair(ok, n2, "FFF", 0.02)
+    for _ in range(2):
+        mb.abcn(s, sp, nl, nlp, dt)
+        mo.abcn(so, spo, nlo, nlpo, dt, ok)
+        assert rel_l2(s.download(), so.e) < 1e-10, (case, "abcn")
+        assert rel_l2(sp.download(), spo.e) < 1e-10
+        assert rel_l2(nlp.download(), nlpo.e) < 1e-15
+        assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
+    s.space = "PPP"
+    with pytest.raises(mb.MlegsError, match="all input scalars must be in FFF"):
+        mb.febe(s, nl, dt)
+
+
+@pytest.mark.parametrize("case", ["gate3d", "chopped", "hyper6"])
+def test_vector_operations(case):
+    kit, ok = _setup(case)
+    fields = [random_ppp(ok, seed=20 + i) for i in range(6)]
+    dev = [mb.Scalar("PPP").upload(f) for f in fields]
+    ora = [mo.Scalar(e=f.copy(order="F"), space="PPP") for f in fields]
+    mb.vecprod(*dev)
+    mo.vecprod(*ora, ok)
+    for d, o in zip(dev[:3], ora[:3]):
+        assert rel_l2(d.download(), o.e) < 1e-14
+    # tp2vec / tp2curlvec on smooth toroidal-poloidal scalars
+    psi_e, chi_e = random_fff(ok, 30), random_fff(ok, 31)
+    psi, psio = _pair(ok, psi_e, "FFF", 0.3)
+    chi, chio = _pair(ok, chi_e, "FFF", -0.2)
+    for fn, fo in ((mb.tp2vec, mo.tp2vec), (mb.tp2curlvec, mo.tp2curlvec)):
+        out = [mb.Scalar("PPP") for _ in range(3)]
+        fn(psi, chi, *out)
+        ref = fo(psio, chio, ok)
+        for d, o in zip(out, ref):
+            assert d.space == "PPP"
+            assert rel_l2(d.download(), o.e) < TOL, (case, fn.__name__)
+    # vec2tp of a generic (not solenoidal) physical field
+    v = [mb.Scalar("PPP").upload(f) for f in fields[:3]]
+    vo = [mo.Scalar(e=f.copy(order="F"), space="PPP") for f in fields[:3]]
+    p2, c2 = mb.Scalar("FFF"), mb.Scalar("FFF")
+    p2o, c2o = mo.scalar_init(ok, "FFF"), mo.scalar_init(ok, "FFF")
+    mb.vec2tp(*v, p2, c2)
+    mo.vec2tp(*vo, p2o, c2o, ok)
+    assert rel_l2(p2.download(), p2o.e) < 1e-10
+    assert rel_l2(c2.download(), c2o.e) < 1e-10
+    assert abs(p2.ln - p2o.ln) <= 1e-12 * max(1.0, abs(p2o.ln))
+    assert abs(c2.ln - c2o.ln) <= 1e-10 * max(1.0, abs(c2o.ln))
+
+
+def test_qvortex_known_answer_on_device():
+    # docs/tutorial/vector_field.md:88: V = (0, (1-exp(-r^2))/r, exp(-r^2)/q) from (psi, chi)
+    p = mb.make_params(48, 8, 4, 48, 5, 3, ell=3.0, zlen=2 * np.pi, visc=1e-3, hyperpow=0, hypervisc=0.0, is_svv=False)
+    kit = mb.TfmKit.init(p)
+    fields = []
+    for amp in (2.0, 1.0):
+        e = np.zeros(kit.glb_sz, dtype=np.complex128, order="F")
+        e[:48, :4, :4] = ((-np.exp(-kit.r ** 2) * amp / (1.0 - kit.x) ** 2) * (1 + 1j))[:, None, None]
+        s = mb.Scalar("PPP").upload(e)
+        mb.trans(s, "FFF")
+        mb.idelsqp(s)
+        mb.zeroat1(s)
+        fields.append(s)
+    psi, chi = fields
+    out = [mb.Scalar("PPP") for _ in range(3)]
+    mb.tp2vec(psi, chi, *out)
+    vr, vp, vz = [o.download() for o in out]
+    r = kit.r
+    assert np.max(np.abs(vp[:48, 0, 0].real - (1.0 - np.exp(-r ** 2)) / r)) < 1e-12
+    assert np.max(np.abs(vz[:48, 0, 0].real - np.exp(-r ** 2))) < 1e-12
+    assert np.max(np.abs(vr[:48, :4, :4])) < 1e-12
+    psi2, chi2 = mb.Scalar("FFF"), mb.Scalar("FFF")
+    mb.vec2tp(*out, psi2, chi2)
+    assert rel_l2(psi2.download(), psi.download()) < 1e-9
+    assert rel_l2(chi2.download(), chi.download()) < 1e-9
+
+
+def test_vortex_time_steps_gate_config():
+    """BASELINE.json configs[2] path at the gate's size (tools/validate_tutorials.py:222-238: nr=32, np=16, nz=8,
+    hyperpow=8, input.params physics): Richardson bootstrap + ABCN steps, parity per step on psi and chi."""
+    nsteps = 5
+    p = mb.make_params(32, 16, 8, 32, 9, 5, ell=4.0, zlen=2 * np.pi, visc=1.0e-4, hyperpow=8, hypervisc=5.0e-7,
+                       is_svv=True, svv_cutoff=0.75, svv_target=2.0e-2, svv_strength=0.12, svv_relax=0.25)
+    kit = mb.TfmKit.init(p)
+    ok = oracle_kit(kit)
+    dt = 1.0e-2
+    psi, chi = vortex.qvort_dist_tp(kit, q=1.0)
+    uz = vortex.uniform_z_fld(kit, b=-0.5)
+    psio, chio = mo.qvort_dist_tp(ok, q=1.0)
+    uzo = mo.uniform_z_fld(ok, b=-0.5)
+    assert rel_l2(psi.download(), psio.e) < TOL and rel_l2(chi.download(), chio.e) < TOL
+    st = vortex.bootstrap(kit, dt, psi, chi, uz)
+    sto = mo.vortex_bootstrap(ok, dt, psio, chio, uzo)
+    errs = []
+    for step in range(nsteps + 1):
+        ep, ec = rel_l2(st.psi.download(), sto.psi.e), rel_l2(st.chi.download(), sto.chi.e)
+        errs.append((ep, ec))
+        assert ep < 1e-10 and ec < 1e-10, (step, errs)
+        assert abs(st.psi.ln - sto.psi.ln) <= 1e-10 * max(1.0, abs(sto.psi.ln))
+        assert abs(st.gain_psi - sto.gain_psi) <= 1e-9
+        if step < nsteps:
+            vortex.step(st, dt)
+            mo.vortex_step(sto, ok, dt)
+    print("per-step rel-L2 (psi, chi):", errs)
