@@ -91,6 +91,9 @@ int mlegs_b200_update_params(const mlegs_params *p);   /* visc, hypervisc, svv_*
 /* space3 selects the layout: "PPP" -> axis_comm (1,0,2) (r sharded), anything else ->
  * (2,1,0) (m sharded); on one rank both are the full (nrdim,npdim,nzdim) block.           */
 int mlegs_b200_field_alloc(mlegs_field *f, const char *space3);
+/* on != 0: later field_alloc calls use cudaMallocManaged (preferred location = the device) so a Fortran
+ * host can keep dereferencing s%e (apps/vortical_flow_3d.f90:136-137, 379); default is cudaMalloc. */
+int mlegs_b200_use_managed(int on);
 int mlegs_b200_field_free(mlegs_field *f);
 int mlegs_b200_field_copy(mlegs_field *dst, const mlegs_field *src);      /* assignment(=) */
 int mlegs_b200_field_zero(mlegs_field *f);

@@ -54,6 +54,7 @@ _SIGS = {
     "mlegs_b200_finalize": (C.c_int, []),
     "mlegs_b200_update_params": (C.c_int, [_P(Params)]),
     "mlegs_b200_field_alloc": (C.c_int, [_P(Field), C.c_char_p]),
+    "mlegs_b200_use_managed": (C.c_int, [C.c_int]),
     "mlegs_b200_field_free": (C.c_int, [_P(Field)]),
     "mlegs_b200_field_copy": (C.c_int, [_P(Field), _P(Field)]),
     "mlegs_b200_field_zero": (C.c_int, [_P(Field)]),

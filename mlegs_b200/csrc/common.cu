@@ -264,6 +264,27 @@ int mlegs_b200_update_params(const mlegs_params *p) {
 static size_t field_elems(const mlegs_field *f) { return (size_t)f->loc_sz[0] * f->loc_sz[1] * f->loc_sz[2]; }
 
 
+static bool g_managed = false;
+
+int mlegs_b200_use_managed(int on) {
+  g_managed = on != 0;
+  return MLEGS_OK;
+}
+
+static int alloc_field_bytes(void **p) {
+  Context &c = ctx();
+  if (!g_managed) {
+    CUDA_TRY(cudaMalloc(p, c.field_bytes));
+    return MLEGS_OK;
+  }
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaMallocManaged(p, c.field_bytes, cudaMemAttachGlobal));
+  CUDA_TRY(cudaMemAdvise(*p, c.field_bytes, cudaMemAdviseSetPreferredLocation, dev));
+  CUDA_TRY(cudaMemPrefetchAsync(*p, c.field_bytes, dev, stream()));
+  return MLEGS_OK;
+}
+
 int mlegs_b200_field_alloc(mlegs_field *f, const char *space3) {
   Context &c = ctx();
   if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
@@ -271,7 +292,7 @@ int mlegs_b200_field_alloc(mlegs_field *f, const char *space3) {
   bool physical = strncmp(space3, "PPP", 3) == 0;
   field_set_layout(f, physical);
   // every field buffer has the size of the larger slab shape so an exchange can reuse it
-  CUDA_TRY(cudaMalloc(&f->e, c.field_bytes));
+  MLEGS_TRY(alloc_field_bytes(&f->e));
   CUDA_TRY(cudaMemsetAsync(f->e, 0, c.field_bytes, stream()));
   f->ln = 0.0;
   memcpy(f->space, space3, 3);
@@ -292,7 +313,7 @@ int mlegs_b200_field_copy(mlegs_field *dst, const mlegs_field *src) {
   if (!src->e) return MLEGS_OK;   // scalar_copy warns and returns, mlegs_scalar_init.f90:107-111
   if (!dst->e) {
     void *keep = nullptr;
-    CUDA_TRY(cudaMalloc(&keep, ctx().field_bytes));
+    MLEGS_TRY(alloc_field_bytes(&keep));
     dst->e = keep;
   }
   void *e = dst->e;
