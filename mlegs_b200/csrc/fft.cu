@@ -258,12 +258,21 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
                      long long stride_pt, int batch1, long long stride_b1, const double *tw, int tw_order,
                      double scale, cudaStream_t st) {
   if (batch0 <= 0 || batch1 <= 0) return MLEGS_OK;
+  static const char *names[4] = {"fft_z_forward", "fft_z_backward", "fft_phi_forward", "fft_phi_backward"};
+  if (fft_reg_supported(plan.n)) {
+    prof_begin(names[(int)mode], st);
+    int rc = launch_fft_reg(mode, plan.n, in, out, batch0 * batch1, batch0, stride_b1, stride_pt, tw, tw_order, scale,
+                            nullptr, 0, 0, st);
+    prof_end(st);
+    MLEGS_TRY(rc);
+    KERNEL_CHECK();
+    return MLEGS_OK;
+  }
   FftPassList pl;
   pl.npass = plan.npass;
   for (int i = 0; i < FFT_MAXPASS; ++i) pl.radix[i] = plan.radix[i];
   dim3 grid((unsigned)((batch0 + plan.ti - 1) / plan.ti), (unsigned)batch1);
   const cplx *twc = reinterpret_cast<const cplx *>(tw);
-  static const char *names[4] = {"fft_z_forward", "fft_z_backward", "fft_phi_forward", "fft_phi_backward"};
   prof_begin(names[(int)mode], st);
   switch (mode) {
     case FFT_C2C_FWD:
@@ -284,6 +293,19 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
       break;
   }
   prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
+                         int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,
+                         cudaStream_t st) {
+  if (nlines <= 0) return MLEGS_OK;
+  if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: compact mode needs the register kernels");
+  prof_begin(mode == FFT_C2C_FWD ? "fft_z_forward" : "fft_z_backward", st);
+  int rc = launch_fft_reg(mode, plan.n, in, out, nlines, 1, 0, stride_pt, tw, tw_order, scale, colstart, ncols, nrl, st);
+  prof_end(st);
+  MLEGS_TRY(rc);
   KERNEL_CHECK();
   return MLEGS_OK;
 }

@@ -1,0 +1,356 @@
+// Register-resident batched line FFTs for power-of-two lengths (32 .. 1024 complex points): the fast
+// path behind launch_fft_lines for the azimuthal (real, packed) and axial (complex) transforms of
+// /root/reference/src/submodules/mlegs_scalar_ops.f90:1567-1848 (dzfft2d / zdfft2d / zfft1d per line).
+//
+// A line of N points is owned by T = N/E threads, each holding E points in registers.  The transform
+// is a Stockham autosort FFT in 2 (N <= 256) or 3 passes of radix <= 16; passes exchange data through
+// one shared-memory tile laid out [point][line] so that every shared access of a quarter warp is one
+// contiguous 128-byte wavefront (conflict free).  The first pass loads straight from HBM and the last
+// pass stores straight to HBM: lanes map to neighbouring lines, which are neighbouring 16-byte elements
+// in memory (the radial index is the fastest one), so global accesses are coalesced 16-byte vectors and
+// every element is read once and written once.  All E loads of a thread are issued before the first
+// butterfly (memory-level parallelism = E x 16 B per thread).
+#include "kernels.h"
+
+namespace mlegs {
+
+namespace {
+
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cplx mul_mi(cplx a) { return make_double2(a.y, -a.x); }   // * (-i)
+// * exp(-i pi/4) = (1 - i)/sqrt(2);  * exp(-3 i pi/4) = (-1 - i)/sqrt(2)
+#define RSQRT2 0.70710678118654752440
+__device__ __forceinline__ cplx mul_w8_1(cplx a) { return make_double2((a.x + a.y) * RSQRT2, (a.y - a.x) * RSQRT2); }
+__device__ __forceinline__ cplx mul_w8_3(cplx a) { return make_double2((a.y - a.x) * RSQRT2, -(a.x + a.y) * RSQRT2); }
+#define C16_1 0.92387953251128675613   // cos(pi/8)
+#define S16_1 0.38268343236508977173   // sin(pi/8)
+
+// natural-order forward (e^{-i}) DFTs of a register array
+template <int R>
+__device__ __forceinline__ void dft(cplx *v);
+
+template <>
+__device__ __forceinline__ void dft<2>(cplx *v) {
+  cplx a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <>
+__device__ __forceinline__ void dft<4>(cplx *v) {
+  cplx a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+  cplx c = cadd(v[1], v[3]), d = mul_mi(csub(v[1], v[3]));
+  v[0] = cadd(a, c);
+  v[1] = cadd(b, d);
+  v[2] = csub(a, c);
+  v[3] = csub(b, d);
+}
+template <>
+__device__ __forceinline__ void dft<8>(cplx *v) {
+  // decimation in frequency: a_i = v_i + v_{i+4}, b_i = (v_i - v_{i+4}) W8^i; X_{2j} = DFT4(a)_j, X_{2j+1} = DFT4(b)_j
+  cplx a[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] = cadd(v[i], v[i + 4]);
+    b[i] = csub(v[i], v[i + 4]);
+  }
+  b[1] = mul_w8_1(b[1]);
+  b[2] = mul_mi(b[2]);
+  b[3] = mul_w8_3(b[3]);
+  dft<4>(a);
+  dft<4>(b);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = a[j];
+    v[2 * j + 1] = b[j];
+  }
+}
+template <>
+__device__ __forceinline__ void dft<16>(cplx *v) {
+  cplx a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = cadd(v[i], v[i + 8]);
+    b[i] = csub(v[i], v[i + 8]);
+  }
+  // W16^i = exp(-i pi i/8)
+  b[1] = cmul(b[1], make_double2(C16_1, -S16_1));
+  b[2] = mul_w8_1(b[2]);
+  b[3] = cmul(b[3], make_double2(S16_1, -C16_1));
+  b[4] = mul_mi(b[4]);
+  b[5] = cmul(b[5], make_double2(-S16_1, -C16_1));
+  b[6] = mul_w8_3(b[6]);
+  b[7] = cmul(b[7], make_double2(-C16_1, -S16_1));
+  dft<8>(a);
+  dft<8>(b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[2 * j] = a[j];
+    v[2 * j + 1] = b[j];
+  }
+}
+
+// One Stockham pass of radix R on the register tile.  Before: v[j] = x[t + T j].  After: v[q + u Q] holds
+// y[out_index(q, u)], out_index = (b - k) R + k + u NS with b = t + q T, k = b mod NS.
+template <int N, int E, int R, int NS>
+__device__ __forceinline__ void pass_compute(cplx (&v)[E], int t, const cplx *__restrict__ tw, int tw_unit) {
+  constexpr int T = N / E, Q = E / R;
+  static_assert(E % R == 0 && N % (NS * R) == 0, "bad pass");
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    cplx x[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) x[u] = v[q + u * Q];
+    if (NS > 1) {
+      const int k = (t + q * T) & (NS - 1);
+      const int step = k * (N / (NS * R)) * tw_unit;
+#pragma unroll
+      for (int u = 1; u < R; ++u) x[u] = cmul(x[u], __ldg(&tw[u * step]));
+    }
+    dft<R>(x);
+#pragma unroll
+    for (int u = 0; u < R; ++u) v[q + u * Q] = x[u];
+  }
+}
+
+template <int N, int E, int R, int NS>
+__device__ __forceinline__ int out_index(int t, int q, int u) {
+  constexpr int T = N / E;
+  const int b = t + q * T;
+  const int k = b & (NS - 1);
+  return (b - k) * R + k + u * NS;
+}
+
+template <int N, int E, int R, int NS, int L>
+__device__ __forceinline__ void pass_to_smem(const cplx (&v)[E], cplx *sm, int t, int l) {
+  constexpr int Q = E / R;
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int u = 0; u < R; ++u) sm[out_index<N, E, R, NS>(t, q, u) * L + l] = v[q + u * Q];
+}
+
+template <int N, int E, int L>
+__device__ __forceinline__ void smem_to_regs(cplx (&v)[E], const cplx *sm, int t, int l) {
+  constexpr int T = N / E;
+#pragma unroll
+  for (int j = 0; j < E; ++j) v[j] = sm[(t + T * j) * L + l];
+}
+
+// radix schedule: R0 = E; R1 = min(E, N/E); R2 = N/(R0 R1) (1 when two passes suffice)
+template <int N, int E>
+struct Sched {
+  static constexpr int R0 = E;
+  static constexpr int R1 = (N / E) < E ? (N / E) : E;
+  static constexpr int R2 = N / (R0 * R1);
+  static_assert(R2 == 1 || R2 == 2 || R2 == 4 || R2 == 8 || R2 == 16, "unsupported length");
+};
+
+}  // namespace
+
+struct FftRegArgs {
+  const cplx *in;
+  cplx *out;
+  long long nlines;      // number of lines handled by this launch
+  long long batch0;      // lines q .. with q / batch0 equal are contiguous in memory
+  long long stride_b1;   // element offset between such runs
+  long long stride_pt;   // element stride between consecutive points of a line
+  const cplx *tw;        // exp(-2 pi i j / tw_order)
+  int tw_order;
+  double scale;
+  const int *colstart;   // compact mode (axial FFT of the retained lines only): prefix sums of nn(m) per column
+  int ncols, nrl;
+};
+
+// MODE: FFT_C2C_FWD / FFT_C2C_BWD / FFT_R2C_FWD / FFT_C2R_BWD (kernels.h).
+template <int MODE, int N, int E, int THREADS>
+__global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
+  constexpr int T = N / E, L = THREADS / T;
+  using S = Sched<N, E>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int l = tid % L, t = tid / L;
+  const long long q = (long long)blockIdx.x * L + l;
+  const bool ok = q < a.nlines;
+  long long base = 0;
+  if (ok) {
+    if (a.colstart) {
+      // column j with colstart[j] <= q < colstart[j+1]
+      int lo = 0, hi = a.ncols;
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if ((long long)__ldg(&a.colstart[mid]) <= q) lo = mid; else hi = mid;
+      }
+      base = (long long)lo * a.nrl + (q - __ldg(&a.colstart[lo]));
+    } else {
+      const long long run = q / a.batch0;
+      base = run * a.stride_b1 + (q - run * a.batch0);
+    }
+  }
+  const cplx *gin = a.in + base;
+  cplx *gout = a.out + base;
+  const int tw_unit = a.tw_order / N;   // 1 for c2c; 2 for the real modes (tw_order == 2N)
+  const cplx zero = make_double2(0.0, 0.0);
+
+  cplx v[E];
+  cplx nyq = zero;   // C_N of the Hermitian input (c2r only)
+
+  if (MODE == FFT_C2R_BWD) {
+    // Hermitian half spectrum C_0..C_N -> shared, then the packed Z_m (conjugated for the conj-FFT-conj inverse).
+    // Im(C_0), Im(C_N) are ignored like external/ffte-7.0/zdfft2d.f:119-128 does.
+#pragma unroll
+    for (int j = 0; j < E; ++j) v[j] = ok ? gin[(long long)(t + T * j) * a.stride_pt] : zero;
+    if (t == 0) nyq = ok ? gin[(long long)N * a.stride_pt] : zero;
+#pragma unroll
+    for (int j = 0; j < E; ++j) sm[(t + T * j) * L + l] = v[j];
+    if (t == 0) sm[N * L + l] = nyq;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int m = t + T * j;
+      cplx cm = v[j];
+      cplx cc = cconj(sm[(N - m) * L + l]);
+      if (m == 0) {
+        cm.y = 0.0;
+        cc.y = 0.0;
+      }
+      cplx s = cadd(cm, cc), d = csub(cm, cc);
+      cplx wm = cconj(__ldg(&a.tw[m]));               // e^{+2 pi i m / (2N)}
+      cplx tt = cmul(wm, d);
+      v[j] = make_double2(s.x - tt.y, -(s.y + tt.x));  // conj(s + i tt)
+    }
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      cplx x = ok ? gin[(long long)(t + T * j) * a.stride_pt] : zero;
+      v[j] = (MODE == FFT_C2C_BWD) ? cconj(x) : x;
+    }
+  }
+
+  // ---- pass 0 ----
+  pass_compute<N, E, S::R0, 1>(v, t, a.tw, tw_unit);
+  pass_to_smem<N, E, S::R0, 1, L>(v, sm, t, l);
+  __syncthreads();
+  smem_to_regs<N, E, L>(v, sm, t, l);
+  // ---- pass 1 ----
+  pass_compute<N, E, S::R1, S::R0>(v, t, a.tw, tw_unit);
+  constexpr bool three = S::R2 > 1;
+  if constexpr (three) {
+    __syncthreads();
+    pass_to_smem<N, E, S::R1, S::R0, L>(v, sm, t, l);
+    __syncthreads();
+    smem_to_regs<N, E, L>(v, sm, t, l);
+    pass_compute<N, E, (three ? S::R2 : 2), S::R0 * S::R1>(v, t, a.tw, tw_unit);
+  }
+  constexpr int RL = three ? S::R2 : S::R1;            // radix of the last pass
+  constexpr int NSL = N / RL;                          // its NS
+
+  if (MODE == FFT_R2C_FWD) {
+    // packed Z -> X_m, m = 0..N (external/ffte-7.0/dzfft2d.f NY=1 branch == rfft), times scale (= 1/np)
+    __syncthreads();
+    pass_to_smem<N, E, RL, NSL, L>(v, sm, t, l);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j <= E; ++j) {
+      if (j == E && t != 0) break;
+      const int m = (j == E) ? N : t + T * j;
+      const int m1 = (m == N) ? 0 : m;
+      const int m2 = (m == 0) ? 0 : N - m;
+      cplx zm = sm[m1 * L + l];
+      cplx zc = cconj(sm[m2 * L + l]);
+      cplx e = make_double2(0.5 * (zm.x + zc.x), 0.5 * (zm.y + zc.y));
+      cplx d = csub(zm, zc);
+      cplx o = make_double2(0.5 * d.y, -0.5 * d.x);   // (-i/2) d
+      cplx x = cadd(e, cmul(__ldg(&a.tw[m]), o));
+      if (ok) gout[(long long)m * a.stride_pt] = make_double2(x.x * a.scale, x.y * a.scale);
+    }
+    return;
+  }
+
+  // ---- last pass straight to HBM ----
+  constexpr int QL = E / RL;
+#pragma unroll
+  for (int qq = 0; qq < QL; ++qq)
+#pragma unroll
+    for (int u = 0; u < RL; ++u) {
+      cplx x = v[qq + u * QL];
+      if (MODE == FFT_C2C_BWD || MODE == FFT_C2R_BWD) x = cconj(x);
+      const int idx = out_index<N, E, RL, NSL>(t, qq, u);
+      if (ok) gout[(long long)idx * a.stride_pt] = make_double2(x.x * a.scale, x.y * a.scale);
+    }
+  if (MODE == FFT_C2R_BWD) {
+    // padding column keeps the Nyquist input times np (quirk Q3; ops:1702-1705)
+    const double fac = (double)(2 * N);
+    if (t == 0 && ok) gout[(long long)N * a.stride_pt] = make_double2(nyq.x * fac, nyq.y * fac);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+template <int N, int E, int THREADS>
+struct RegCfg {
+  static constexpr int T = N / E, L = THREADS / T;
+  static constexpr size_t smem = (size_t)(N + 1) * L * sizeof(cplx);
+};
+
+template <int MODE, int N, int E, int THREADS>
+static int launch_one(const FftRegArgs &a, cudaStream_t st) {
+  using C = RegCfg<N, E, THREADS>;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(fft_reg_kernel<MODE, N, E, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)C::smem));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)((a.nlines + C::L - 1) / C::L);
+  fft_reg_kernel<MODE, N, E, THREADS><<<grid, THREADS, C::smem, st>>>(a);
+  return MLEGS_OK;
+}
+
+template <int MODE>
+static int launch_mode(int n, const FftRegArgs &a, cudaStream_t st) {
+  switch (n) {
+    case 32: return launch_one<MODE, 32, 8, 256>(a, st);
+    case 64: return launch_one<MODE, 64, 8, 256>(a, st);
+    case 128: return launch_one<MODE, 128, 16, 256>(a, st);
+    case 256: return launch_one<MODE, 256, 16, 256>(a, st);
+    case 512: return launch_one<MODE, 512, 16, 512>(a, st);
+    case 1024: return launch_one<MODE, 1024, 16, 512>(a, st);
+  }
+  return fail(MLEGS_E_ARG, "fft_reg: unsupported length");
+}
+
+bool fft_reg_supported(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
+
+int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
+                   long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
+                   const int *colstart, int ncols, int nrl, cudaStream_t st) {
+  FftRegArgs a;
+  a.in = in;
+  a.out = out;
+  a.nlines = nlines;
+  a.batch0 = batch0;
+  a.stride_b1 = stride_b1;
+  a.stride_pt = stride_pt;
+  a.tw = reinterpret_cast<const cplx *>(tw);
+  a.tw_order = tw_order;
+  a.scale = scale;
+  a.colstart = colstart;
+  a.ncols = ncols;
+  a.nrl = nrl;
+  switch (mode) {
+    case FFT_C2C_FWD: return launch_mode<FFT_C2C_FWD>(n, a, st);
+    case FFT_C2C_BWD: return launch_mode<FFT_C2C_BWD>(n, a, st);
+    case FFT_R2C_FWD: return launch_mode<FFT_R2C_FWD>(n, a, st);
+    case FFT_C2R_BWD: return launch_mode<FFT_C2R_BWD>(n, a, st);
+  }
+  return MLEGS_OK;
+}
+
+}  // namespace mlegs

@@ -22,6 +22,16 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
                      long long stride_pt, int batch1, long long stride_b1, const double *tw, int tw_order,
                      double scale, cudaStream_t st);
 
+// fft_reg.cu: register-resident fast path for power-of-two lengths 32..1024
+bool fft_reg_supported(int n);
+int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
+                   long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
+                   const int *colstart, int ncols, int nrl, cudaStream_t st);
+// axial FFT of the retained lines only (rows < nn(m) of each local column); colstart = device prefix sums
+int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
+                         int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,
+                         cudaStream_t st);
+
 // ---- legendre.cu -----------------------------------------------------------------------
 struct LegArgs {
   const cplx *in;

@@ -128,6 +128,12 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   }
   __syncthreads();
   const int fr = lane >> 2, fk = lane & 3;
+  // The warp's four 8-row tiles are interleaved with the other row-warp's (tile index 2 mt + wr), and tiles
+  // that lie entirely beyond the truncation nn(m) are skipped: both row-warps (hence all four SM sub-partitions)
+  // keep the same number of DMMAs when nn is not a multiple of the 128-row CTA tile.
+  int nact = 0;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) nact += (n0 + 2 * ((2 * mt + wr) * 8) + par < nn) ? 1 : 0;
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
     if (c + 1 < nchunks) gload(c + 1);
@@ -135,22 +141,24 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
     for (int ks = 0; ks < LEG_KC / 4; ++ks) {
       double af[4], bf[4];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) af[mt] = sm[buf].A[par][wr * 32 + mt * 8 + fr][ks * 4 + fk];
+      for (int mt = 0; mt < 4; ++mt) af[mt] = sm[buf].A[par][(2 * mt + wr) * 8 + fr][ks * 4 + fk];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) bf[nt] = sm[buf].B[par ^ a.swap_parity][wc * 32 + nt * 8 + fr][ks * 4 + fk];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
+        if (mt < nact) {
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
     }
     if (c + 1 < nchunks) sstore(buf ^ 1);
     __syncthreads();
   }
 
-  // epilogue: thread holds C[row = mt*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex
+  // epilogue: thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
-    int n = n0 + 2 * (wr * 32 + mt * 8 + fr) + par;
+    int n = n0 + 2 * ((2 * mt + wr) * 8 + fr) + par;
     if (n >= a.nrdim) continue;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {

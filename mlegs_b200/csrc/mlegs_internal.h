@@ -87,6 +87,10 @@ struct Context {
   void *d_solve_ws = nullptr;    // banded-solve workspace (U factors)
   size_t solve_ws_bytes = 0;
   FftPlan plan_p, plan_z;
+  // compact axial FFT: prefix sums of nn(m) over the local columns, cached per (nrc, npc)
+  int *d_colstart = nullptr;
+  int cs_nrc = -1, cs_npc = -1, cs_ncols = 0;
+  long long cs_total = 0;
   void *stream = nullptr;        // cudaStream_t
   // multi-GPU
   void *d_window = nullptr;      // exchange window (field-sized), exported over CUDA IPC

@@ -3,7 +3,9 @@
 // kernels.  On one rank the two scalar_exchange calls are pure re-labellings (the block already is
 // the whole (nrdim, npdim, nzdim) array); on several ranks the (2,1)/(1,2) exchange is the
 // all-to-all in dist.cu and the (1,3)/(3,1) exchange is a no-op in the slab layout.
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "kernels.h"
 
@@ -67,6 +69,37 @@ int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
                           c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st);
 }
 
+// Axial FFT restricted to the retained lines (rows < nn(m) of every local column m < npc).  Valid when the
+// other lines are known zeros that stay in place (forward, right after rtrans_forward) or are never read
+// again (backward, right before rtrans_backward).
+static int stage_z_compact(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+  Context &c = ctx();
+  cudaStream_t st = (cudaStream_t)c.stream;
+  const int nrc = c.p.nrchop + s->nrchop_offset, npc = c.p.npchop + s->npchop_offset;
+  const int npl = s->loc_sz[1], m0 = s->loc_st[1];
+  if (c.cs_nrc != nrc || c.cs_npc != npc || c.cs_ncols != npl || !c.d_colstart) {
+    std::vector<int> h(npl + 1, 0);
+    for (int j = 0; j < npl; ++j) {
+      int m = m0 + j;
+      int nn = (m < npc) ? std::max(std::min(nrc, nrc - m), 0) : 0;
+      nn = std::min(nn, s->loc_sz[0]);
+      h[j + 1] = h[j] + nn;
+    }
+    if (c.d_colstart) CUDA_TRY(cudaFree(c.d_colstart));
+    c.d_colstart = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&c.d_colstart, (npl + 1) * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(c.d_colstart, h.data(), (npl + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // h goes out of scope
+    c.cs_nrc = nrc;
+    c.cs_npc = npc;
+    c.cs_ncols = npl;
+    c.cs_total = h[npl];
+  }
+  long long plane = (long long)s->loc_sz[0] * s->loc_sz[1];
+  return launch_fft_z_compact(forward ? FFT_C2C_FWD : FFT_C2C_BWD, c.plan_z, src, dst, c.d_colstart, npl, s->loc_sz[0],
+                              c.cs_total, plane, c.d_tw_z, c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st);
+}
+
 int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
   LegArgs a;
   MLEGS_TRY(rtrans_args(s, forward ? "rtrans_forward" : "rtrans_backward", &a));
@@ -88,6 +121,8 @@ int trans_impl(mlegs_field *s, const char *to) {
   const bool has_p = c.p.np > 1, has_z = c.p.nz > 1;
   const bool multi = c.nranks > 1 && has_p;
 
+  const bool compact_ok = has_z && fft_reg_supported(c.plan_z.n);
+  bool rows_zero = false;
   cplx *home = (cplx *)s->e;
   cplx *tmp = (cplx *)c.d_scratch[0];
   cplx *at = home;   // where the data currently lives
@@ -103,8 +138,9 @@ int trans_impl(mlegs_field *s, const char *to) {
             MLEGS_TRY(exchange_slab(s, 2, 1, at, other(at)));
             at = other(at);
           } else {
-            // without an axial stage, go out of place so that the Legendre stage lands back at home
-            cplx *o = (!has_z && dst >= 2) ? other(at) : at;
+            // go out of place when the Legendre stage follows, so that it lands back at home and the axial
+            // stage can then run in place on the retained lines only
+            cplx *o = (dst >= 2) ? other(at) : at;
             MLEGS_TRY(stage_phi(s, true, at, o));
             at = o;
           }
@@ -112,10 +148,14 @@ int trans_impl(mlegs_field *s, const char *to) {
       } else if (cur == 1) {
         MLEGS_TRY(stage_r(s, true, at, other(at)));   // ln removal (ops:193-195) is fused into the load
         at = other(at);
+        rows_zero = true;                             // rows >= nn(m) are exact zeros now
       } else if (cur == 2) {
         if (has_z) {
           cplx *o = (at == home) ? at : home;   // land at home whenever possible
-          MLEGS_TRY(stage_z(s, true, at, o));
+          if (rows_zero && o == at && compact_ok)
+            MLEGS_TRY(stage_z_compact(s, true, at, o));
+          else
+            MLEGS_TRY(stage_z(s, true, at, o));
           at = o;
         }
       }
@@ -128,7 +168,10 @@ int trans_impl(mlegs_field *s, const char *to) {
         if (has_z) {
           // if the Legendre stage follows, go out of place so that it lands back at home
           cplx *o = (dst <= 1) ? other(at) : at;
-          MLEGS_TRY(stage_z(s, false, at, o));
+          if (dst <= 1 && compact_ok)
+            MLEGS_TRY(stage_z_compact(s, false, at, o));   // rtrans_backward reads the retained rows only
+          else
+            MLEGS_TRY(stage_z(s, false, at, o));
           at = o;
         }
       } else if (cur == 2) {

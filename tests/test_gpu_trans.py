@@ -15,6 +15,12 @@ CASES = {
     "gate3d": (32, 16, 8, 32, 9, 5, 4.0, 8),           # tools/validate_tutorials.py:222-238
     "radix35": (36, 30, 20, 30, 12, 9, 2.0, 4),        # np, nz with factors 3 and 5; chops below the maximum
     "cube64": (64, 64, 64, 64, 33, 33, 4.0, 0),
+    # every length of the register-resident FFT kernels (fft_reg.cu): np/2 and nz in {32 .. 1024}
+    "fft256": (16, 512, 256, 16, 9, 129, 4.0, 0),
+    "fftp512": (8, 1024, 32, 8, 5, 17, 4.0, 0),
+    "fftz512": (8, 64, 512, 8, 5, 257, 4.0, 0),
+    "fftp1024": (8, 2048, 32, 8, 5, 17, 4.0, 0),
+    "fftz1024": (8, 64, 1024, 8, 5, 513, 4.0, 0),
 }
 TOL = 1.0e-12   # BASELINE.json north_star: 1e-12 relative L2 per transform
 
@@ -63,6 +69,21 @@ def test_full_transforms_and_ln_term(case):
         mb.trans(s, "PPP")
         mb.trans(s, "FFF")
         assert rel_l2(s.download(), e1) < 50 * TOL
+
+
+@pytest.mark.parametrize("case", ["cube64", "gate3d"])
+def test_axial_stage_alone_transforms_every_line(case):
+    """Forward trans does not chop: FFP -> FFF on its own must transform rows beyond the
+    truncation too, while inside a full trans only the retained lines are touched (compact path)."""
+    kit, ok = _setup(case)
+    rng = np.random.default_rng(7)
+    e0 = np.asfortranarray(rng.standard_normal(kit.glb_sz) + 1j * rng.standard_normal(kit.glb_sz))
+    for a, b in (("FFP", "FFF"), ("FFF", "FFP")):
+        s = mb.Scalar(a).upload(e0)
+        so = mo.Scalar(e=e0.copy(order="F"), space=a)
+        mb.trans(s, b)
+        mo.trans(so, b, ok)
+        assert rel_l2(s.download(), so.e) < TOL, (case, a, b)
 
 
 def test_chop_offsets_in_rtrans():
