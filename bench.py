@@ -9,8 +9,9 @@ input in cache ("inputs larger than L2").  GDOF/s = NF*NR*NP*NZ / t_step / 1e9.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--size S]
 
-N > 1 is launched by torchrun, one rank per GPU; fields are independent scalars, so the batch is
-sharded across ranks with no data-path collective (weak scaling: NF fields per GPU).
+N > 1 is launched by torchrun, one rank per GPU; every field is slab-distributed over all ranks like the
+reference's MPI run (one all-to-all per one-way transform, over NVLink peer memory) and the batch grows with
+N so that per-GPU work is fixed (weak scaling: NF field-equivalents per GPU).
 """
 from __future__ import annotations
 
@@ -185,27 +186,34 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)     # its "NCCL version" banner goes to stdout; stdout carries ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = workload(args.size)
     p = mb.make_params(wl["nr"], wl["np"], wl["nz"], wl["nrchop"], wl["npchop"], wl["nzchop"], ell=wl["ell"],
                        zlen=wl["zlen"])
-    kit = mb.TfmKit.init(p)
+    # N > 1: every field is slab-distributed over all ranks like the reference's MPI run (PPP sharded in r,
+    # spectral spaces in m); each one-way transform then contains one all-to-all over NVLink peer memory.
+    kit = mb.TfmKit.init(p, rank, world)
+    if world > 1:
+        mb.dist.attach()
     dof = wl["nr"] * wl["np"] * wl["nz"]
     field_bytes = int(np.prod(kit.glb_sz)) * 16
-    nf = args.fields or max(2, int(np.ceil(2.2 * 126e6 / field_bytes)))   # batch > 2x L2
+    # fields per GPU-equivalent: the batch is > 2x L2 and long enough for the clock sampler to see it
+    nf = args.fields or max(2, int(np.ceil(2.2 * 126e6 / field_bytes)), min(64, int(1.2e9 // field_bytes)))
+    nfields = nf * world          # weak scaling: per-GPU work (nf field-equivalents) is fixed
     stream = torch.cuda.Stream()
     mb.set_stream(stream.cuda_stream)
 
     okit = oracle_kit(kit)
-    e0 = mo.Scalar(e=random_fff(okit, seed=rank), space="FFF")
+    e0 = random_fff(okit, seed=0)
     fields = []
     with torch.cuda.stream(stream):
-        s0 = mb.Scalar("FFF").upload(e0.e)
+        s0 = mb.Scalar("FFF").upload_global(e0)
         mb.trans(s0, "PPP")
         fields.append(s0)
-        for _ in range(nf - 1):
+        for _ in range(nfields - 1):
             fields.append(s0.copy())
     mb.device_sync()
 
@@ -219,12 +227,14 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    if rank == 0:
+        sampler.rows.clear()      # keep only the samples of the timed region
     mb.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -241,7 +251,7 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * nf * dof / (ms_step * 1e-3) / 1e9
+    value = nfields * dof / (ms_step * 1e-3) / 1e9
 
     # ---- per-kernel CUDA-event timing of the same workload (separate pass, not the headline number) ----
     mb.prof_enable(True)
@@ -250,12 +260,11 @@ def run_native(args):
     prof = mb.prof_report()
     mb.prof_enable(False)
     tot = sum(v["ms"] for v in prof.values())
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    dur_ms = prof[dom]["ms"] / prof[dom]["launches"]
     nr, npn, nz = wl["nr"], wl["np"], wl["nz"]
     nrdim, npdim = kit.glb_sz[0], kit.glb_sz[1]
     S = sum(max(wl["nrchop"] - m, 0) for m in range(wl["npchop"]))
-    # algorithmic bytes per launch (stated in DESIGN.md)
+    # algorithmic bytes / flops per launch of ONE whole field; a rank
+    # of a slab-distributed run processes 1/world of that per launch
     alg_bytes = {
         "fft_phi_forward": 8 * nr * npn * nz + 16 * nr * npdim * nz,
         "fft_phi_backward": 8 * nr * npn * nz + 16 * nr * npdim * nz,
@@ -263,24 +272,53 @@ def run_native(args):
         "fft_z_backward": 2 * 16 * nz * S,
         "legendre_forward": 16 * nr * wl["npchop"] * nz + 16 * S * nz,
         "legendre_backward": 16 * nr * wl["npchop"] * nz + 16 * S * nz,
+        "exchange_21": 2 * 16 * nrdim * npdim * nz,
+        "exchange_12": 2 * 16 * nrdim * npdim * nz,
     }
-    peak, peak_src = measured_peaks()
-    achieved = alg_bytes[dom] / (dur_ms * 1e-3) / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": dur_ms, "share_of_step": prof[dom]["ms"] / tot,
-                "kernels": {k: {"avg_ms": v["ms"] / v["launches"], "share": v["ms"] / tot,
-                                "alg_GBps": alg_bytes[k] / (v["ms"] / v["launches"] * 1e-3) / 1e9,
-                                "legendre_TFLOPs": (2.0 * nr * nz * S / (v["ms"] / v["launches"] * 1e-3) / 1e12
-                                                    if k.startswith("legendre") else None)}
-                            for k, v in prof.items()}}
+    leg_flops = 2.0 * nr * nz * S
+    hbm_peak, hbm_src = measured_peaks()
+    dmma_peak = mb.dmma_peak()
+    kernels = {}
+    for k, v in prof.items():
+        avg_ms = v["ms"] / v["launches"]
+        ent = {"avg_ms": avg_ms, "share": v["ms"] / tot, "launches": v["launches"]}
+        if k in alg_bytes:
+            ent["alg_GBps"] = alg_bytes[k] / world / (avg_ms * 1e-3) / 1e9
+            ent["hbm_frac"] = ent["alg_GBps"] / hbm_peak
+        if k.startswith("legendre"):
+            ent["TFLOPs"] = leg_flops / world / (avg_ms * 1e-3) / 1e12
+            ent["fp64_tensor_frac"] = ent["TFLOPs"] / dmma_peak
+        kernels[k] = ent
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = kernels[dom]
+    if dom.startswith("legendre") and d["fp64_tensor_frac"] >= d["hbm_frac"]:
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": d["TFLOPs"], "peak": dmma_peak, "unit": "TFLOP/s",
+                    "frac": d["fp64_tensor_frac"], "traffic": None,
+                    "peak_source": "FP64 DMMA m8n8k4 micro-benchmark measured live in this run "
+                                   "(mlegs_b200_dmma_peak; MEASURED_PEAKS.json has no FP64 entry)"}
+    else:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": d["alg_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": d["hbm_frac"], "traffic": None, "peak_source": hbm_src}
+    roofline.update({"avg_launch_ms": d["avg_ms"], "share_of_step": d["share"], "dmma_peak_tflops": dmma_peak,
+                     "kernels": kernels})
+    traffic_file = os.path.join(ROOT, "profiles", "r1", "traffic.json")
+    if os.path.exists(traffic_file) and world == 1:
+        tr = json.load(open(traffic_file)).get(str(args.size), {})
+        roofline["traffic"] = tr.get(dom)
+        roofline["traffic_source"] = tr.get("source")
 
     # ---- e2e: the reference-facing host-buffer entry, pinned host arrays, H2D+D2H inside the timed region ----
+    n_ppp = int(np.prod(fields[0].loc_sz))
+    mb.trans(fields[0], "FFF")
+    n_fff = int(np.prod(fields[0].loc_sz))
+    mb.trans(fields[0], "PPP")
+    nhost = max(n_ppp, n_fff)
+    ne2e = min(len(fields), 16 * world)
     hosts = []
-    for s in fields:
-        h = torch.empty(int(np.prod(kit.glb_sz)) * 2, dtype=torch.float64).pin_memory()
-        a = h.numpy().view(np.complex128).reshape(kit.glb_sz, order="F")
-        a[...] = s.download()
+    for s in fields[:ne2e]:
+        h = torch.empty(nhost * 2, dtype=torch.float64).pin_memory()
+        a = h.numpy().view(np.complex128)
+        a[:n_ppp] = s.download().ravel(order="F")
         hosts.append((h, a))
 
     def e2e_step():
@@ -300,9 +338,10 @@ def run_native(args):
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e = {"value": world * nf * dof / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": 2 * nf * field_bytes,
-           "d2h_bytes_per_step": 2 * nf * field_bytes, "ms_per_step": e2e_ms,
-           "api": "mlegs_b200_trans_host (host s%e in, host s%e out), pinned host arrays"}
+    e2e = {"value": ne2e * dof / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": ne2e * 16 * (n_ppp + n_fff), "d2h_bytes_per_step": ne2e * 16 * (n_ppp + n_fff),
+           "ms_per_step": e2e_ms, "fields_per_step": ne2e,
+           "api": "mlegs_b200_trans_host (host s%e in, host s%e out), pinned host arrays; bytes are per rank"}
 
     # ---- CPU baseline on rank 0: bounded sample of the same workload with the oracle port ----
     cpu = None
@@ -314,16 +353,23 @@ def run_native(args):
                          "one field per thread"}
 
     if rank == 0:
+        par = "single GPU" if world == 1 else (f"every field slab-distributed over {world} GPUs (r / m shards), "
+                                               "one peer-memory all-to-all per one-way transform")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"PPP<->FFF round trip {args.size}^3 (BASELINE.json configs[1])",
-                           "fields_per_step_per_gpu": nf, "l2_policy": f"inputs larger than L2: {nf} distinct fields "
-                           f"x {field_bytes / 1e6:.1f} MB per GPU", "parallelism": f"independent scalars x{world}",
+                           "fields_per_step": nfields, "fields_per_step_per_gpu": nf,
+                           "l2_policy": f"inputs larger than L2: {nfields} distinct fields x {field_bytes / 1e6:.1f} MB "
+                                        f"({nf * field_bytes / 1e6:.0f} MB per GPU)",
+                           "parallelism": par,
                            **{k: (float(v) if isinstance(v, float) else v) for k, v in wl.items()}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
         print(json.dumps(line), flush=True)
     if dist is not None:
+        mb.device_sync()
+        dist.barrier()
+        mb.dist.detach()
         dist.destroy_process_group()
 
 

@@ -70,6 +70,9 @@ long long mlegs_b200_launch_count(int reset);
  * {"kernel": {"launches": n, "ms": total}, ...} and clears the records */
 int mlegs_b200_prof_enable(int on);
 int mlegs_b200_prof_report(char *buf, size_t nbuf);
+/* measured FP64 tensor-pipe (DMMA m8n8k4) throughput of this device in TFLOP/s: the roofline denominator of the
+ * Legendre kernels (MEASURED_PEAKS.json has no FP64 entry) */
+int mlegs_b200_dmma_peak(double *tflops);
 
 /* ---- transform kit: host tables (tfm%init(), sinit:6-154) ---------------------------- */
 /* sizes: x,w,ln,r: nr;  lognorm: (nrchop+14)*npchop;  pf: (nr/2)*(nrchop+14)*npchop;
@@ -160,6 +163,14 @@ int mlegs_b200_is_finite(const mlegs_field *s, int *all_finite);
 int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64[64]);
 int mlegs_b200_dist_attach(const unsigned char *handles64_all_ranks);
 int mlegs_b200_dist_detach(void);
+/* Host-only exchange plan (no CUDA needed): destination rank and linear index in that rank's new local block
+ * for every element of rank `rank`'s local block in memory order; dir 0 = exchange(2,1), 1 = exchange(1,2).
+ * The device put kernel runs the same addressing code (dist:395-504's subarray datatypes). */
+int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim, int nz, int *dst_rank,
+                            long long *dst_index);
+/* Sum n HOST doubles over all ranks on the library's own peer windows (the app-level MPI_Allreduce of
+ * check_stability, apps/vortical_flow_3d.f90:404); identical result on every rank; no-op on one rank. */
+int mlegs_b200_dist_allreduce(double *host_inout, int n);
 
 #ifdef __cplusplus
 }

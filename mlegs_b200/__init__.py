@@ -8,3 +8,4 @@ from ._lib import MlegsError, Params, Field, lib, LIB_PATH   # noqa: F401
 from .kit import TfmKit, make_params, finalize               # noqa: F401
 from .scalar import *                                         # noqa: F401,F403
 from .scalar import Scalar                                    # noqa: F401
+from . import dist                                            # noqa: F401,E402

@@ -49,6 +49,7 @@ _SIGS = {
     "mlegs_b200_launch_count": (C.c_longlong, [C.c_int]),
     "mlegs_b200_prof_enable": (C.c_int, [C.c_int]),
     "mlegs_b200_prof_report": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "mlegs_b200_dmma_peak": (C.c_int, [_P(C.c_double)]),
     "mlegs_b200_tfm_tables": (C.c_int, [_P(Params)] + [C.c_void_p] * 9),
     "mlegs_b200_init": (C.c_int, [_P(Params)] + [C.c_void_p] * 6 + [C.c_int, C.c_int]),
     "mlegs_b200_finalize": (C.c_int, []),
@@ -93,6 +94,8 @@ _SIGS = {
     "mlegs_b200_dist_window": (C.c_int, [_P(C.c_void_p), _P(C.c_size_t), C.c_void_p]),
     "mlegs_b200_dist_attach": (C.c_int, [C.c_void_p]),
     "mlegs_b200_dist_detach": (C.c_int, []),
+    "mlegs_b200_dist_allreduce": (C.c_int, [C.c_void_p, C.c_int]),
+    "mlegs_b200_dist_put_map": (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
 }
 
 

@@ -1,24 +1,237 @@
-// scalar_exchange (/root/reference/src/submodules/mlegs_scalar_dist.f90:6-67) in the slab layout.
+// scalar_exchange (/root/reference/src/submodules/mlegs_scalar_dist.f90:6-67, 468-504) in the slab layout,
+// as one-sided puts over NVLink peer memory instead of MPI_Alltoallw with derived datatypes.
+//
+// Every rank owns one CUDA-IPC-exported allocation ("window"):
+//     [ flags | reduction slots (2 parities) | W0 | W1 ]
+// W0/W1 are field-sized receive buffers used alternately (epoch parity).  An exchange is ONE kernel:
+// each rank scatters its local block straight into the peers' W[epoch & 1] with coalesced 16-byte stores
+// (the transposition the MPI datatypes describe is done by the addressing), fences at system scope, and the
+// last CTA publishes `epoch` into every peer's arrive[] slot and waits until all peers have published
+// theirs.  Double buffering makes that single barrier sufficient: a peer can only write W[p] again two
+// epochs later, after it has seen this rank's signal of the epoch in between, which this rank sends (in
+// stream order) after its readers of W[p] have finished.
+//
+// The tiny all-reduces of the reference (SVV energies ops:117-118, calcat ops:265,302, ln ops:394,657,748)
+// use the same mechanism on the reduction slots and sum in rank order on every rank, so all ranks hold
+// bit-identical results.
+#include <cstring>
+
 #include "kernels.h"
 
 namespace mlegs {
 
-// Move the local block from `src` to `dst` so that axis_new becomes local and axis_old distributed.
-int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, void *dst) {
-  Context &c = ctx();
-  if (s->axis_comm[axis_old - 1] != 0)
-    return fail(MLEGS_E_COMM,
-                "ERROR: scalar_exchange requires the data to be non-distributed along the old dimension");
-  if (c.nranks == 1) {
-    if (src != dst) {
-      size_t n = (size_t)s->loc_sz[0] * s->loc_sz[1] * s->loc_sz[2];
-      CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(cplx), cudaMemcpyDeviceToDevice, (cudaStream_t)c.stream));
-    }
-    s->axis_comm[axis_old - 1] = s->axis_comm[axis_new - 1];
-    s->axis_comm[axis_new - 1] = 0;
-    return MLEGS_OK;
+#define DIST_MAX_RANKS 16
+#define DIST_FLAG_BYTES 4096
+#define DIST_RED_DOUBLES 16384                      // per rank and parity (>= 2 nz)
+#define DIST_SPIN_LIMIT (1ll << 31)                 // ~1-2 s of clock64 ticks before giving up
+
+struct WinHeader {                                  // lives at the start of every window
+  unsigned long long arrive[DIST_MAX_RANKS];        // data barrier: epoch published by rank q
+  unsigned long long red_arrive[DIST_MAX_RANKS];    // reduction barrier
+};
+
+static size_t win_red_offset() { return DIST_FLAG_BYTES; }
+static size_t win_data_offset() {
+  return DIST_FLAG_BYTES + (size_t)2 * DIST_MAX_RANKS * DIST_RED_DOUBLES * sizeof(double);
+}
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct DistState {
+  bool attached = false;
+  void *base[DIST_MAX_RANKS] = {nullptr};           // window base of every rank as mapped here
+  unsigned long long epoch = 0, red_epoch = 0;
+  unsigned int *d_ctr = nullptr;                    // local CTA counter (last-block detection)
+  size_t wstride = 0;                               // bytes of one W buffer
+};
+static DistState g_dist;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.global.release.sys.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.global.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Destination of local element (i, j, k) of rank `me` in an exchange: owning rank q and linear index inside
+// q's new local block.  Shared by the put kernel and the host-side plan (mlegs_b200_dist_put_map), which the
+// CPU tests check against the reference's subarray semantics (dist:395-504).
+// dir 0: (2,1) exchange, src (r_loc, npdim, nz) -> (nrdim, m_cnt[q], nz);  dir 1: (1,2), src (nrdim, m_loc, nz)
+// -> (r_cnt[q], npdim, nz).
+__host__ __device__ inline void slab_put_index(int dir, int me, int nranks, const int *r_cnt, const int *r_off,
+                                               const int *m_cnt, const int *m_off, int nrdim, int npdim, int i, int j,
+                                               int k, int *q_out, size_t *dst_out) {
+  int q = 0;
+  if (dir == 0) {
+    while (q + 1 < nranks && j >= m_off[q + 1]) ++q;
+    *dst_out = ((size_t)k * m_cnt[q] + (j - m_off[q])) * nrdim + r_off[me] + i;
+  } else {
+    while (q + 1 < nranks && i >= r_off[q + 1]) ++q;
+    *dst_out = ((size_t)k * npdim + m_off[me] + j) * r_cnt[q] + (i - r_off[q]);
   }
-  return fail(MLEGS_E_COMM, "scalar_exchange: multi-rank exchange window is not attached");
+  *q_out = q;
+}
+
+struct PeerTable {
+  void *base[DIST_MAX_RANKS];
+  int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
+  int rank, nranks;
+  size_t data_off;      // byte offset of W[parity] inside a window
+  unsigned long long epoch;
+  unsigned int *ctr;
+  int *flag;            // device error flags ([2] = exchange timeout)
+};
+
+// publish `epoch` to all peers and wait for theirs; called by one thread of the last CTA
+__device__ void barrier_publish_wait(const PeerTable &t, bool reduction) {
+  for (int q = 0; q < t.nranks; ++q) {
+    WinHeader *h = reinterpret_cast<WinHeader *>(t.base[q]);
+    st_release_sys(reduction ? &h->red_arrive[t.rank] : &h->arrive[t.rank], t.epoch);
+  }
+  WinHeader *me = reinterpret_cast<WinHeader *>(t.base[t.rank]);
+  for (int q = 0; q < t.nranks; ++q) {
+    const unsigned long long *p = reduction ? &me->red_arrive[q] : &me->arrive[q];
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < t.epoch) {
+      if (clock64() - t0 > DIST_SPIN_LIMIT) {
+        atomicOr(t.flag + 2, 1);
+        break;
+      }
+    }
+  }
+}
+
+// dir 0: (2,1) exchange, src (r_loc, npdim, nz) -> peers' (nrdim, m_cnt[q], nz)   [phi local -> r local]
+// dir 1: (1,2) exchange, src (nrdim, m_loc, nz) -> peers' (r_cnt[q], npdim, nz)   [r local -> phi local]
+__global__ void __launch_bounds__(256) exchange_put_kernel(PeerTable t, const cplx *__restrict__ src, int dir, int nrdim,
+                                                           int npdim, int nz) {
+  const int me = t.rank;
+  const int rows = dir == 0 ? t.r_cnt[me] : nrdim;
+  const int cols = dir == 0 ? npdim : t.m_cnt[me];
+  const size_t n = (size_t)rows * cols * nz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % rows);
+    const size_t r = idx / rows;
+    const int j = (int)(r % cols);
+    const int k = (int)(r / cols);
+    int q;
+    size_t dst;
+    slab_put_index(dir, me, t.nranks, t.r_cnt, t.r_off, t.m_cnt, t.m_off, nrdim, npdim, i, j, k, &q, &dst);
+    cplx *w = reinterpret_cast<cplx *>(reinterpret_cast<char *>(t.base[q]) + t.data_off);
+    w[dst] = src[idx];
+  }
+  // all puts of this CTA are visible system-wide before the CTA is counted
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(t.ctr, 1u);
+    if (prev == gridDim.x - 1) {
+      *t.ctr = 0;
+      __threadfence_system();
+      barrier_publish_wait(t, false);
+    }
+  }
+}
+
+// sum over ranks of `n` doubles, in rank order, result on every rank (one CTA)
+__global__ void allreduce_small_kernel(PeerTable t, double *inout, int n, size_t red_off) {
+  for (int q = 0; q < t.nranks; ++q) {
+    double *slot = reinterpret_cast<double *>(reinterpret_cast<char *>(t.base[q]) + red_off) +
+                   (size_t)t.rank * DIST_RED_DOUBLES;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = inout[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) barrier_publish_wait(t, true);
+  __syncthreads();
+  const double *mine = reinterpret_cast<const double *>(reinterpret_cast<char *>(t.base[t.rank]) + red_off);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = 0.0;
+    for (int q = 0; q < t.nranks; ++q) acc += *((volatile const double *)&mine[(size_t)q * DIST_RED_DOUBLES + i]);
+    inout[i] = acc;
+  }
+}
+
+static void fill_table(PeerTable *t) {
+  Context &c = ctx();
+  memset(t, 0, sizeof(*t));
+  for (int q = 0; q < c.nranks; ++q) {
+    t->base[q] = g_dist.base[q];
+    t->r_cnt[q] = c.r_cnt[q];
+    t->r_off[q] = c.r_off[q];
+    t->m_cnt[q] = c.m_cnt[q];
+    t->m_off[q] = c.m_off[q];
+  }
+  t->rank = c.rank;
+  t->nranks = c.nranks;
+  t->ctr = g_dist.d_ctr;
+  t->flag = c.d_flag;
+}
+
+bool dist_active() { return ctx().nranks > 1 && g_dist.attached; }
+
+// Sum `n` device doubles over all ranks (no-op on one rank).
+int dist_allreduce(double *d_inout, int n) {
+  Context &c = ctx();
+  if (c.nranks == 1) return MLEGS_OK;
+  if (!g_dist.attached) return fail(MLEGS_E_COMM, "mlegs_b200: multi-rank run without attached exchange windows");
+  if (n > DIST_RED_DOUBLES) return fail(MLEGS_E_ARG, "dist_allreduce: too many values");
+  PeerTable t;
+  fill_table(&t);
+  t.epoch = ++g_dist.red_epoch;
+  size_t red_off = win_red_offset() + (size_t)(t.epoch & 1) * DIST_MAX_RANKS * DIST_RED_DOUBLES * sizeof(double);
+  cudaStream_t st = (cudaStream_t)c.stream;
+  prof_begin("allreduce_small", st);
+  allreduce_small_kernel<<<1, 256, 0, st>>>(t, d_inout, n, red_off);
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+// Move the local block at `src` so that axis_new becomes local and axis_old distributed.  On return *landed
+// points at the buffer holding the new local block (the receive window on several ranks, `src` on one).
+int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, void **landed) {
+  Context &c = ctx();
+  *landed = const_cast<void *>(src);
+  if (c.nranks == 1) return MLEGS_OK;
+  if (!g_dist.attached) return fail(MLEGS_E_COMM, "scalar_exchange: multi-rank exchange window is not attached");
+  int dir;
+  if (axis_old == 2 && axis_new == 1)
+    dir = 0;
+  else if (axis_old == 1 && axis_new == 2)
+    dir = 1;
+  else
+    return fail(MLEGS_E_COMM, "scalar_exchange: the slab layout only exchanges axes (2,1) and (1,2)");
+  PeerTable t;
+  fill_table(&t);
+  t.epoch = ++g_dist.epoch;
+  t.data_off = win_data_offset() + (size_t)(t.epoch & 1) * g_dist.wstride;
+  const size_t n = (size_t)s->loc_sz[0] * s->loc_sz[1] * s->loc_sz[2];
+  unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  if (grid == 0) grid = 1;
+  cudaStream_t st = (cudaStream_t)c.stream;
+  prof_begin(dir == 0 ? "exchange_21" : "exchange_12", st);
+  exchange_put_kernel<<<grid, 256, 0, st>>>(t, (const cplx *)src, dir, c.nrdim, c.npdim, c.nzdim);
+  prof_end(st);
+  KERNEL_CHECK();
+  *landed = reinterpret_cast<char *>(g_dist.base[c.rank]) + t.data_off;
+  int keep[3] = {s->axis_comm[0], s->axis_comm[1], s->axis_comm[2]};
+  field_set_layout(s, dir == 1);          // new local sizes / offsets
+  s->axis_comm[0] = keep[0];              // the labels are the caller's business (reference: dist:52-58)
+  s->axis_comm[1] = keep[1];
+  s->axis_comm[2] = keep[2];
+  return MLEGS_OK;
+}
+
+int dist_check_timeout() {
+  Context &c = ctx();
+  if (c.nranks == 1) return MLEGS_OK;
+  int h[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h, c.d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)c.stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)c.stream));
+  if (h[2]) return fail(MLEGS_E_COMM, "scalar_exchange: timed out waiting for a peer rank");
+  return MLEGS_OK;
 }
 
 }  // namespace mlegs
@@ -32,21 +245,120 @@ int mlegs_b200_exchange(mlegs_field *s, int axis_old, int axis_new) {
   if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
   if (axis_old < 1 || axis_old > 3 || axis_new < 1 || axis_new > 3 || axis_old == axis_new)
     return fail(MLEGS_E_COMM, "scalar_exchange: invalid axes");
-  if (s->axis_comm[axis_new - 1] == 0) {
-    // nothing is distributed along axis_new: the reference would index comm_grps(0); treat as a no-op
-    return MLEGS_OK;
+  const int g_new = s->axis_comm[axis_new - 1];
+  if (g_new == 0) return MLEGS_OK;   // nothing is distributed along axis_new (the reference would index comm_grps(0))
+  if (s->axis_comm[axis_old - 1] != 0)   // dist:16-20
+    return fail(MLEGS_E_COMM,
+                "ERROR: scalar_exchange requires the data to be non-distributed along the old dimension");
+  if (c.nranks > 1 && g_new == 1) {
+    // comm_grps(1) holds all the ranks of the slab decomposition: a real all-to-all
+    void *landed = nullptr;
+    MLEGS_TRY(exchange_slab(s, axis_old, axis_new, s->e, &landed));
+    if (landed != s->e) {
+      size_t n = (size_t)s->loc_sz[0] * s->loc_sz[1] * s->loc_sz[2];
+      CUDA_TRY(cudaMemcpyAsync(s->e, landed, n * sizeof(cplx), cudaMemcpyDeviceToDevice, (cudaStream_t)c.stream));
+    }
   }
-  return exchange_slab(s, axis_old, axis_new, s->e, s->e);
+  // comm_grps(2) (and everything on one rank) is a single-rank group: the exchange is a re-labelling (dist:52-58)
+  s->axis_comm[axis_old - 1] = g_new;
+  s->axis_comm[axis_new - 1] = 0;
+  return MLEGS_OK;
 }
 
 int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64[64]) {
-  (void)dev_ptr; (void)bytes; (void)handle64;
-  return fail(MLEGS_E_STATE, "mlegs_b200_dist_window: not implemented yet");
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  if (c.nranks > DIST_MAX_RANKS) return fail(MLEGS_E_COMM, "mlegs_b200: at most 16 ranks per node are supported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  static_assert(sizeof(WinHeader) <= DIST_FLAG_BYTES, "header size");
+  if (!c.d_window) {
+    g_dist.wstride = align256(c.field_bytes);
+    size_t total = win_data_offset() + 2 * g_dist.wstride;
+    CUDA_TRY(cudaMalloc(&c.d_window, total));
+    CUDA_TRY(cudaMemset(c.d_window, 0, win_data_offset()));
+    CUDA_TRY(cudaMalloc((void **)&g_dist.d_ctr, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(g_dist.d_ctr, 0, sizeof(unsigned int)));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c.d_window));
+  memcpy(handle64, &h, 64);
+  if (dev_ptr) *dev_ptr = c.d_window;
+  if (bytes) *bytes = win_data_offset() + 2 * g_dist.wstride;
+  return MLEGS_OK;
 }
-int mlegs_b200_dist_attach(const unsigned char *h) {
-  (void)h;
-  return fail(MLEGS_E_STATE, "mlegs_b200_dist_attach: not implemented yet");
+
+int mlegs_b200_dist_attach(const unsigned char *handles64_all_ranks) {
+  Context &c = ctx();
+  if (!c.ready || !c.d_window) return fail(MLEGS_E_STATE, "mlegs_b200_dist_attach: call mlegs_b200_dist_window first");
+  for (int q = 0; q < c.nranks; ++q) {
+    if (q == c.rank) {
+      g_dist.base[q] = c.d_window;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles64_all_ranks + (size_t)64 * q, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(&g_dist.base[q], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  g_dist.epoch = g_dist.red_epoch = 0;
+  g_dist.attached = true;
+  return MLEGS_OK;
 }
-int mlegs_b200_dist_detach(void) { return MLEGS_OK; }
+
+int mlegs_b200_dist_detach(void) {
+  Context &c = ctx();
+  if (g_dist.attached) {
+    cudaDeviceSynchronize();
+    for (int q = 0; q < c.nranks; ++q)
+      if (q != c.rank && g_dist.base[q]) cudaIpcCloseMemHandle(g_dist.base[q]);
+  }
+  if (c.d_window) cudaFree(c.d_window);
+  c.d_window = nullptr;
+  if (g_dist.d_ctr) cudaFree(g_dist.d_ctr);
+  g_dist = DistState();
+  return MLEGS_OK;
+}
+
+/* Host-only (no CUDA): the exchange plan of rank `rank` out of `nranks` for global sizes (nrdim, npdim, nz):
+ * for every element of the local block, in memory order, the destination rank and the linear index inside
+ * that rank's new local block.  Same code as the device put kernel. */
+int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim, int nz, int *dst_rank,
+                            long long *dst_index) {
+  if (nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks || (dir != 0 && dir != 1))
+    return fail(MLEGS_E_COMM, "mlegs_b200_dist_put_map: bad arguments");
+  int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
+  for (int q = 0; q < nranks; ++q) {
+    decompose(nrdim, nranks, q, &r_cnt[q], &r_off[q]);
+    decompose(npdim, nranks, q, &m_cnt[q], &m_off[q]);
+  }
+  const int rows = dir == 0 ? r_cnt[rank] : nrdim;
+  const int cols = dir == 0 ? npdim : m_cnt[rank];
+  size_t idx = 0;
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < cols; ++j)
+      for (int i = 0; i < rows; ++i, ++idx) {
+        int q;
+        size_t dst;
+        slab_put_index(dir, rank, nranks, r_cnt, r_off, m_cnt, m_off, nrdim, npdim, i, j, k, &q, &dst);
+        dst_rank[idx] = q;
+        dst_index[idx] = (long long)dst;
+      }
+  return MLEGS_OK;
+}
+
+/* sum `n` HOST doubles over all ranks (the app-level MPI_Allreduce of e.g. check_stability,
+ * apps/vortical_flow_3d.f90:404, expressed on the library's own peer windows) */
+int mlegs_b200_dist_allreduce(double *host_inout, int n) {
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  if (c.nranks == 1) return MLEGS_OK;
+  if (n > Context::RED_DOUBLES) return fail(MLEGS_E_ARG, "mlegs_b200_dist_allreduce: too many values");
+  cudaStream_t st = (cudaStream_t)c.stream;
+  CUDA_TRY(cudaMemcpyAsync(c.d_red, host_inout, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  MLEGS_TRY(dist_allreduce(c.d_red, n));
+  CUDA_TRY(cudaMemcpyAsync(host_inout, c.d_red, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return dist_check_timeout();
+}
 
 }  // extern "C"

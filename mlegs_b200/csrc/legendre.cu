@@ -13,8 +13,10 @@
 //
 // A CTA owns one (m, 32 complex columns) strip and a 128-row (forward: n, both parities) or
 // 64-row (backward: i, both parity accumulators) output tile; the contraction runs in chunks of 16
-// through shared memory with register-staged prefetch of the next chunk.  8 warps: 2 parities x
-// (2 x 2) warp tiles of 32 x 32, 16 DMMA tiles per warp per k-step.
+// through a two-stage cp.async (LDGSTS) pipeline: the table slice and the RAW field data of chunk c+1
+// stream into shared memory while the tensor pipe works on chunk c, and the parity fold (f(i) +- f(nr-1-i))
+// times the quadrature weight is applied when the B fragments are read.  8 warps: 2 parities x (2 x 2)
+// warp tiles of 32 x 32, 16 DMMA tiles per warp per k-step.
 #include "kernels.h"
 
 namespace mlegs {
@@ -40,11 +42,36 @@ __device__ __forceinline__ int nn_of_m(int mglob, int nrc, int npc) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// asynchronous global -> shared copies (LDGSTS); src_bytes == 0 zero-fills the destination
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int nbytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int nbytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(nbytes) : "memory");
+}
+// DRAM -> L2 prefetch of a contiguous range (bytes: multiple of 16, 16-byte aligned address); no smem involved
+__device__ __forceinline__ void l2_prefetch(const void *gmem, int bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
+#define LEG_PD 3   // chunks of field data kept in flight towards L2 ahead of the cp.async stage
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+#define LEG_LDB_F (2 * LEG_KC + 8)       // doubles per kz row of the raw (unfolded) data tiles: conflict-free fragments
 struct FwdSmem {
   double A[2][LEG_MT_F / 2][LEG_LD];     // [parity][row within parity][k]
-  double B[2][2 * LEG_NTC][LEG_LD];      // [fold: 0 even(+), 1 odd(-)][real column][k]
+  double T[LEG_NTC][LEG_LDB_F];          // raw top rows    f(i, kz), i = chunk rows, (re, im) interleaved
+  double Bm[LEG_NTC][LEG_LDB_F];         // raw mirror rows f(nr-1-i, kz)
+  double W[LEG_KC];                      // quadrature weights of the chunk rows
 };
 
 __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) {
@@ -62,6 +89,8 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   cplx *out = a.out + (size_t)ml * a.nrl;
   const double *pf = a.pf + (size_t)mglob * a.nrh * a.ne;
   const bool use_ln = (mglob == 0) && (a.lnval != 0.0);
+  const bool have_w = a.w != nullptr;
+  const bool vec2 = (a.nrh & 1) == 0;                  // table rows are 16-byte aligned
 
   double acc[4][4][2];
 #pragma unroll
@@ -72,61 +101,61 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   const bool active = (n0 < nn);
   const int nchunks = active ? (a.nrh + LEG_KC - 1) / LEG_KC : 0;
 
-  // staging registers: A: 128 rows x 16 k = 2048 doubles -> 8 per thread; thread -> (k = tid & 15, rows tid>>4 + 16 j)
-  // B: 32 kz x 16 i -> 512 (top,bottom) complex pairs -> 2 per thread; thread -> (i = tid & 15, kz = tid>>4 + 16 j)
-  double ra[8];
-  cplx rbe[2], rbo[2];
-  const int lk = tid & 15, lr = tid >> 4;
-
-  auto gload = [&](int c) {
-    const int kk = c * LEG_KC + lk;     // i index
-    const bool kok = kk < a.nrh;
+  // Stage chunk c (rows i = c*KC .. +KC of the half grid) into buffer `buf`; out-of-range pieces are zero-filled.
+  auto issue = [&](int c, int buf) {
+    FwdSmem &S = sm[buf];
+    const int i0 = c * LEG_KC;
+    // A: 128 table rows x KC doubles
+    if (vec2) {
+      // 128 x 8 16-byte pieces -> 4 per thread
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int n = n0 + lr + 16 * j;
-      ra[j] = (kok && n < nn) ? __ldg(&pf[(size_t)n * a.nrh + kk]) : 0.0;
-    }
-    double wi = kok ? (a.w ? __ldg(&a.w[kk]) : 1.0) : 0.0;
-    double l1 = 0.0, l2 = 0.0;
-    if (use_ln && kok) {
-      l1 = a.lnval * __ldg(&a.lnx[kk]);
-      l2 = a.lnval * __ldg(&a.lnx[a.nr - 1 - kk]);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      int kz = kz0 + lr + 16 * j;
-      cplx top = make_double2(0.0, 0.0), bot = make_double2(0.0, 0.0);
-      if (kok && kz < a.nzl) {
-        top = in[(size_t)kz * col_stride + kk];
-        bot = in[(size_t)kz * col_stride + (a.nr - 1 - kk)];
-        top.x -= l1;
-        bot.x -= l2;
+      for (int j = 0; j < 4; ++j) {
+        const int p = tid + LEG_THREADS * j;
+        const int r = p >> 3, k2 = (p & 7) * 2;
+        const int n = n0 + r;
+        const bool ok = (n < nn) && (i0 + k2 < a.nrh);
+        cp_async16(&S.A[r & 1][r >> 1][k2], ok ? (const void *)&pf[(size_t)n * a.nrh + i0 + k2] : (const void *)pf, ok);
       }
-      rbe[j] = make_double2((top.x + bot.x) * wi, (top.y + bot.y) * wi);
-      rbo[j] = make_double2((top.x - bot.x) * wi, (top.y - bot.y) * wi);
-    }
-  };
-  auto sstore = [&](int buf) {
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int r = lr + 16 * j;             // row within tile; n0 is even so parity(r) == parity(n)
-      sm[buf].A[r & 1][r >> 1][lk] = ra[j];
+      for (int j = 0; j < 8; ++j) {
+        const int p = tid + LEG_THREADS * j;
+        const int r = p >> 4, k = p & 15;
+        const int n = n0 + r;
+        const bool ok = (n < nn) && (i0 + k < a.nrh);
+        cp_async8(&S.A[r & 1][r >> 1][k], ok ? (const void *)&pf[(size_t)n * a.nrh + i0 + k] : (const void *)pf, ok);
+      }
     }
+    // raw data: 32 kz x KC complex, top and mirrored rows -> 2 + 2 per thread
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      int c = 2 * (lr + 16 * j);
-      sm[buf].B[0][c][lk] = rbe[j].x;
-      sm[buf].B[0][c + 1][lk] = rbe[j].y;
-      sm[buf].B[1][c][lk] = rbo[j].x;
-      sm[buf].B[1][c + 1][lk] = rbo[j].y;
+      const int p = tid + LEG_THREADS * j;
+      const int kzl = p >> 4, k = p & 15;
+      const int kz = kz0 + kzl, i = i0 + k;
+      const bool ok = (kz < a.nzl) && (i < a.nrh);
+      const cplx *col = in + (size_t)kz * col_stride;
+      cp_async16(&S.T[kzl][2 * k], ok ? (const void *)&col[i] : (const void *)in, ok);
+      cp_async16(&S.Bm[kzl][2 * k], ok ? (const void *)&col[a.nr - 1 - i] : (const void *)in, ok);
+    }
+    if (have_w && tid < LEG_KC) {
+      const bool ok = i0 + tid < a.nrh;
+      cp_async8(&S.W[tid], ok ? (const void *)&a.w[i0 + tid] : (const void *)a.w, ok);
     }
   };
 
-  if (nchunks > 0) {
-    gload(0);
-    sstore(0);
-  }
-  __syncthreads();
+  // The field columns of this CTA are streamed exactly once and come from DRAM in 256-byte pieces: keep LEG_PD
+  // chunks of them on their way into L2 so that the cp.async stage only ever sees L2 latency.
+  auto prefetch = [&](int c) {
+    if (tid < 2 * LEG_NTC) {
+      const int kz = kz0 + (tid & (LEG_NTC - 1)), i0 = c * LEG_KC;
+      if (c < nchunks && kz < a.nzl && i0 < a.nrh) {
+        const int cnt = min(LEG_KC, a.nrh - i0);
+        const cplx *col = in + (size_t)kz * col_stride;
+        l2_prefetch((tid >> 5) ? (const void *)&col[a.nr - i0 - cnt] : (const void *)&col[i0], cnt * 16);
+      }
+    }
+  };
+
   const int fr = lane >> 2, fk = lane & 3;
   // The warp's four 8-row tiles are interleaved with the other row-warp's (tile index 2 mt + wr), and tiles
   // that lie entirely beyond the truncation nn(m) are skipped: both row-warps (hence all four SM sub-partitions)
@@ -134,16 +163,52 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   int nact = 0;
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) nact += (n0 + 2 * ((2 * mt + wr) * 8) + par < nn) ? 1 : 0;
+  const bool minus = (par ^ a.swap_parity) != 0;        // fold sign: even rows take f(i) + f(mirror), odd rows the difference
+  const int bre = fr & 1;                               // this lane's real column is the re (0) or im (1) part
+
+  if (nchunks > 0) {
+    issue(0, 0);
+    cp_async_commit();
+#pragma unroll
+    for (int d = 1; d <= LEG_PD; ++d) prefetch(d);
+  }
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
-    if (c + 1 < nchunks) gload(c + 1);
+    cp_async_wait_all();
+    __syncthreads();            // chunk c has landed for everyone; everyone is done reading buffer buf^1
+    if (c + 1 < nchunks) {
+      issue(c + 1, buf ^ 1);
+      cp_async_commit();
+      prefetch(c + 1 + LEG_PD);
+    }
+    const FwdSmem &S = sm[buf];
 #pragma unroll
     for (int ks = 0; ks < LEG_KC / 4; ++ks) {
+      const int k = ks * 4 + fk;
       double af[4], bf[4];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) af[mt] = sm[buf].A[par][(2 * mt + wr) * 8 + fr][ks * 4 + fk];
+      for (int mt = 0; mt < 4; ++mt) af[mt] = S.A[par][(2 * mt + wr) * 8 + fr][k];
+      double wk = have_w ? S.W[k] : 1.0;
+      double l1 = 0.0, l2 = 0.0;
+      if (use_ln && bre == 0) {   // log term removed from the real part of the m = 0 column (ops:193-195)
+        const int i = c * LEG_KC + k;
+        if (i < a.nrh) {
+          l1 = a.lnval * __ldg(&a.lnx[i]);
+          l2 = a.lnval * __ldg(&a.lnx[a.nr - 1 - i]);
+        }
+      }
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bf[nt] = sm[buf].B[par ^ a.swap_parity][wc * 32 + nt * 8 + fr][ks * 4 + fk];
+      for (int nt = 0; nt < 4; ++nt) {
+        const int kzl = (wc * 32 + nt * 8 + fr) >> 1;
+        double t = S.T[kzl][2 * k + bre];
+        double b = S.Bm[kzl][2 * k + bre];
+        if (use_ln) {
+          t -= l1;
+          b -= l2;
+        }
+        double f = minus ? (t - b) : (t + b);
+        bf[nt] = have_w ? f * wk : f;
+      }
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
         if (mt < nact) {
@@ -151,29 +216,40 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
           for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
     }
-    if (c + 1 < nchunks) sstore(buf ^ 1);
-    __syncthreads();
   }
 
-  // epilogue: thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex
+  // epilogue: thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex.
+  // The two parities interleave along n, so the tile goes through shared memory and leaves as contiguous
+  // 16-byte-per-lane rows (n fastest), 2 KB per kz column.
+  __syncthreads();            // everyone is done with the staging buffers
+  cplx(*cs)[LEG_MT_F + 2] = reinterpret_cast<cplx(*)[LEG_MT_F + 2]>(smraw);
+  static_assert(sizeof(cplx) * LEG_NTC * (LEG_MT_F + 2) <= 2 * sizeof(FwdSmem), "epilogue smem");
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
-    int n = n0 + 2 * ((2 * mt + wr) * 8 + fr) + par;
-    if (n >= a.nrdim) continue;
+    const int nl = 2 * ((2 * mt + wr) * 8 + fr) + par;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      int kz = kz0 + (wc * 32 + nt * 8) / 2 + fk;
-      if (kz < a.nzl) out[(size_t)kz * col_stride + n] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      const int kzl = (wc * 32 + nt * 8) / 2 + fk;
+      cs[kzl][nl] = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
     }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < LEG_MT_F * LEG_NTC / LEG_THREADS; ++j) {
+    const int p = tid + LEG_THREADS * j;
+    const int nl = p & (LEG_MT_F - 1), kzl = p / LEG_MT_F;
+    const int n = n0 + nl, kz = kz0 + kzl;
+    if (n < a.nrdim && kz < a.nzl) out[(size_t)kz * col_stride + n] = cs[kzl][nl];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+#define LEG_LDB_B (4 * LEG_KC + 2)       // doubles per kz row of the raw coefficient tile (32 complex + pad)
 struct BwdSmem {
   double A[2][LEG_KC][LEG_LDA_B];        // [parity][k (coefficient pair index)][i]
-  double B[2][2 * LEG_NTC][LEG_LD];      // [parity][real column][k]
+  double B[LEG_NTC][LEG_LDB_B];          // raw coefficients a(n, kz), n = 32 consecutive, (re, im) interleaved
 };
 
 __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a) {
@@ -191,6 +267,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
   cplx *out = a.out + (size_t)ml * a.nrl;
   const double *pf = a.pf + (size_t)mglob * a.nrh * a.ne;
   const bool use_ln = (mglob == 0) && (a.lnval != 0.0);
+  const bool vec2 = (a.nrh & 1) == 0;
 
   double acc[4][4][2];
 #pragma unroll
@@ -201,67 +278,83 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
   const int kpairs = (nn + 1) / 2;                       // contraction length of the even parity (>= odd)
   const int nchunks = (kpairs + LEG_KC - 1) / LEG_KC;
 
-  // A staging: 2 parities x 16 k x 64 i = 2048 doubles -> 8 per thread; thread -> (i = tid & 63, q = tid >> 6 (0..3))
-  //            element j: kk2 = q + 4 j (0..31) -> (parity = kk2 & 1, k = kk2 >> 1): consecutive n
-  // B staging: 32 consecutive n x 32 kz complex = 1024 -> 4 per thread; thread -> (nloc = tid & 31, kz = tid>>5 + 8 j)
-  double ra[8];
-  cplx rb[4];
-  const int li = tid & 63, lq = tid >> 6;
-  const int lnl = tid & 31, lkz = tid >> 5;
-
-  auto gload = [&](int c) {
+  auto issue = [&](int c, int buf) {
+    BwdSmem &S = sm[buf];
     const int nbase = c * 2 * LEG_KC;                    // first coefficient index n of this chunk
-    const int ii = i0 + li;
+    // A: 32 consecutive n x 64 i doubles
+    if (vec2) {
+      // 32 x 32 16-byte pieces -> 4 per thread
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int n = nbase + lq + 4 * j;
-      ra[j] = (ii < a.nrh && n < nn) ? __ldg(&pf[(size_t)n * a.nrh + ii]) : 0.0;
+      for (int j = 0; j < 4; ++j) {
+        const int p = tid + LEG_THREADS * j;
+        const int nl = p >> 5, i2 = (p & 31) * 2;
+        const int n = nbase + nl, ii = i0 + i2;
+        const bool ok = (n < nn) && (ii < a.nrh);
+        cp_async16(&S.A[nl & 1][nl >> 1][i2], ok ? (const void *)&pf[(size_t)n * a.nrh + ii] : (const void *)pf, ok);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int p = tid + LEG_THREADS * j;
+        const int nl = p >> 6, il = p & 63;
+        const int n = nbase + nl, ii = i0 + il;
+        const bool ok = (n < nn) && (ii < a.nrh);
+        cp_async8(&S.A[nl & 1][nl >> 1][il], ok ? (const void *)&pf[(size_t)n * a.nrh + ii] : (const void *)pf, ok);
+      }
     }
+    // raw coefficients: 32 kz x 32 n complex -> 4 per thread
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int n = nbase + lnl;
-      int kz = kz0 + lkz + 8 * j;
-      rb[j] = (n < nn && kz < a.nzl) ? in[(size_t)kz * col_stride + n] : make_double2(0.0, 0.0);
-    }
-  };
-  auto sstore = [&](int buf) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int k2 = lq + 4 * j;
-      sm[buf].A[k2 & 1][k2 >> 1][li] = ra[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int c = 2 * (lkz + 8 * j);
-      sm[buf].B[lnl & 1][c][lnl >> 1] = rb[j].x;
-      sm[buf].B[lnl & 1][c + 1][lnl >> 1] = rb[j].y;
+      const int p = tid + LEG_THREADS * j;
+      const int kzl = p >> 5, nl = p & 31;
+      const int kz = kz0 + kzl, n = nbase + nl;
+      const bool ok = (kz < a.nzl) && (n < nn);
+      cp_async16(&S.B[kzl][2 * nl], ok ? (const void *)&in[(size_t)kz * col_stride + n] : (const void *)in, ok);
     }
   };
 
-  if (nchunks > 0) {
-    gload(0);
-    sstore(0);
-  }
-  __syncthreads();
+  auto prefetch = [&](int c) {   // DRAM -> L2 for the coefficient columns, LEG_PD chunks ahead (512-byte pieces)
+    if (tid < LEG_NTC) {
+      const int kz = kz0 + tid, nb = c * 2 * LEG_KC;
+      if (c < nchunks && kz < a.nzl && nb < nn) {
+        const int cnt = min(2 * LEG_KC, nn - nb);
+        l2_prefetch(&in[(size_t)kz * col_stride + nb], cnt * 16);
+      }
+    }
+  };
   const int fr = lane >> 2, fk = lane & 3;
+  const int bre = fr & 1;
+  if (nchunks > 0) {
+    issue(0, 0);
+    cp_async_commit();
+#pragma unroll
+    for (int d = 1; d <= LEG_PD; ++d) prefetch(d);
+  }
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
-    if (c + 1 < nchunks) gload(c + 1);
+    cp_async_wait_all();
+    __syncthreads();
+    if (c + 1 < nchunks) {
+      issue(c + 1, buf ^ 1);
+      cp_async_commit();
+      prefetch(c + 1 + LEG_PD);
+    }
+    const BwdSmem &S = sm[buf];
 #pragma unroll
     for (int ks = 0; ks < LEG_KC / 4; ++ks) {
+      const int k = ks * 4 + fk;
       double af[4], bf[4];
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) af[mt] = sm[buf].A[par][ks * 4 + fk][wr * 32 + mt * 8 + fr];
+      for (int mt = 0; mt < 4; ++mt) af[mt] = S.A[par][k][wr * 32 + mt * 8 + fr];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) bf[nt] = sm[buf].B[par][wc * 32 + nt * 8 + fr][ks * 4 + fk];
+      for (int nt = 0; nt < 4; ++nt) bf[nt] = S.B[(wc * 32 + nt * 8 + fr) >> 1][2 * (2 * k + par) + bre];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
-    if (c + 1 < nchunks) sstore(buf ^ 1);
-    __syncthreads();
   }
+  __syncthreads();   // everyone is done with the staging buffers before they are reused below
 
   // combine parities through shared memory: C[par][i (64)][real col (64)], padded
   double(*cs)[LEG_MT_B][2 * LEG_NTC + 2] = reinterpret_cast<double(*)[LEG_MT_B][2 * LEG_NTC + 2]>(smraw);

@@ -12,6 +12,8 @@
 namespace mlegs {
 
 int trans_impl(mlegs_field *s, const char *to);
+int dist_allreduce(double *d_inout, int n);   // dist.cu: sum over ranks, identical result everywhere
+int dist_check_timeout();
 int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst);
 int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst);
 
@@ -49,6 +51,17 @@ static int read_elem(const mlegs_field *s, size_t off, cplx *out) {
   CUDA_TRY(cudaMemcpyAsync(out, (const cplx *)s->e + off, sizeof(cplx), cudaMemcpyDeviceToHost, strm()));
   CUDA_TRY(cudaStreamSynchronize(strm()));
   return MLEGS_OK;
+}
+
+// sum of host doubles over all ranks (MPI_Allreduce of ops:394, 657, 748); no-op on one rank
+static int allreduce_host(double *v, int n) {
+  Context &c = ctx();
+  if (c.nranks == 1) return MLEGS_OK;
+  CUDA_TRY(cudaMemcpyAsync(c.d_red, v, n * sizeof(double), cudaMemcpyHostToDevice, strm()));
+  MLEGS_TRY(dist_allreduce(c.d_red, n));
+  CUDA_TRY(cudaMemcpyAsync(v, c.d_red, n * sizeof(double), cudaMemcpyDeviceToHost, strm()));
+  CUDA_TRY(cudaStreamSynchronize(strm()));
+  return dist_check_timeout();
 }
 
 // log-term coefficients of del^2 P_L_0^0: 4/3, -2, 2/3 over ell^2 exp(lognorm(.,1)) (ops:562-566)
@@ -139,6 +152,7 @@ int svv_impl(mlegs_field *s, double *gain) {
   a.strength = 0.0;
   const double target = std::max(c.p.svv_target, 1.0e-12);
   MLEGS_TRY(launch_svv_energy(a, c.d_red + 16, c.d_red, strm()));
+  MLEGS_TRY(dist_allreduce(c.d_red, 2));   // MPI_Allreduce of ops:117-118
   CUDA_TRY(cudaMemcpyAsync(c.h_red, c.d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, strm()));
   CUDA_TRY(cudaStreamSynchronize(strm()));
   double total = c.h_red[0], tail = c.h_red[1];
@@ -182,6 +196,7 @@ static int calcat_device(const mlegs_field *s, const double *d_at, bool subtract
 static int calcat_host(const mlegs_field *s, const double *d_at, double *out) {
   Context &c = ctx();
   MLEGS_TRY(calcat_device(s, d_at, false, nullptr));
+  MLEGS_TRY(dist_allreduce(c.d_red, 2 * s->loc_sz[2]));   // MPI_Allreduce of ops:265, 302
   CUDA_TRY(cudaMemcpyAsync(out, c.d_red, 2 * s->loc_sz[2] * sizeof(double), cudaMemcpyDeviceToHost, strm()));
   CUDA_TRY(cudaStreamSynchronize(strm()));
   return MLEGS_OK;
@@ -210,6 +225,7 @@ int delsqp_impl(mlegs_field *s, bool inverse) {
     MLEGS_TRY(read_elem(s, 0, &v));
     ln_new = v.x * ell2 * std::exp(c.h_lognorm[0]);   // ops:392
   }
+  if (inverse) MLEGS_TRY(allreduce_host(&ln_new, 1));   // ops:394
   MLEGS_TRY(launch_delsqp((cplx *)s->e, s->loc_sz[0], s->loc_sz[1], s->loc_sz[2], s->loc_st[1], ci.nrc, ci.npc,
                           ell2, inverse ? 1 : 0, strm()));
   if (own) {
@@ -403,10 +419,15 @@ int idel2_impl(mlegs_field *s, int have_preln, double preln) {
   a.sp2 = 2.0 / 3.0 / ell2 * std::exp(c.h_lognorm[0] - c.h_lognorm[2]);
   a.preln_rhs = preln / std::exp(c.h_lognorm[0]);
   MLEGS_TRY(solve_two_ranges(a, ci, s->loc_sz[2], have_preln ? 3 : 2));
-  if (owns_m0(s) && ci.npc >= 1 && ci.nrc >= 1 && ci.nzc >= 1) {
-    cplx v;
-    MLEGS_TRY(read_elem(s, 0, &v));
-    s->ln = v.x * std::exp(c.h_lognorm[0]);   // ops:625, 716
+  if (ci.npc >= 1 && ci.nrc >= 1 && ci.nzc >= 1) {
+    double lnv = 0.0;
+    if (owns_m0(s)) {
+      cplx v;
+      MLEGS_TRY(read_elem(s, 0, &v));
+      lnv = v.x * std::exp(c.h_lognorm[0]);   // ops:625, 716
+    }
+    MLEGS_TRY(allreduce_host(&lnv, 1));       // ops:657, 748
+    s->ln = lnv;
   }
   return MLEGS_OK;
 }

@@ -11,7 +11,7 @@
 
 namespace mlegs {
 
-int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, void *dst);   // dist.cu
+int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, void **landed);   // dist.cu
 
 static int space_id(const char *sp) {
   if (!strncmp(sp, "PPP", 3)) return 0;
@@ -22,9 +22,13 @@ static int space_id(const char *sp) {
 }
 static const char *kSpaceName[4] = {"PPP", "PFP", "FFP", "FFF"};
 
+// space label + the axis_comm labels the reference's trans leaves behind (ops:185-233 with the exchanges of
+// dist:52-58): PPP (1,0,2), PFP/FFP (0,1,2), FFF (2,1,0)
 static void set_space(mlegs_field *s, int id) {
   memcpy(s->space, kSpaceName[id], 3);
   s->space[3] = 0;
+  static const int labels[4][3] = {{1, 0, 2}, {0, 1, 2}, {0, 1, 2}, {2, 1, 0}};
+  for (int a = 0; a < 3; ++a) s->axis_comm[a] = labels[id][a];
 }
 
 static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
@@ -135,8 +139,9 @@ int trans_impl(mlegs_field *s, const char *to) {
           if (multi) {
             // FFT in place, then the (2,1) exchange moves the block into the other buffer
             MLEGS_TRY(stage_phi(s, true, at, at));
-            MLEGS_TRY(exchange_slab(s, 2, 1, at, other(at)));
-            at = other(at);
+            void *landed = nullptr;
+            MLEGS_TRY(exchange_slab(s, 2, 1, at, &landed));   // lands in this rank's receive window
+            at = (cplx *)landed;
           } else {
             // go out of place when the Legendre stage follows, so that it lands back at home and the axial
             // stage can then run in place on the retained lines only
@@ -180,8 +185,9 @@ int trans_impl(mlegs_field *s, const char *to) {
       } else if (cur == 1) {
         if (has_p) {
           if (multi) {
-            MLEGS_TRY(exchange_slab(s, 1, 2, at, other(at)));
-            at = other(at);
+            void *landed = nullptr;
+            MLEGS_TRY(exchange_slab(s, 1, 2, at, &landed));
+            at = (cplx *)landed;
             cplx *o = home;
             MLEGS_TRY(stage_phi(s, false, at, o));
             at = o;

@@ -1,6 +1,7 @@
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 
 #include "kernels.h"
@@ -41,6 +42,25 @@ void prof_end(cudaStream_t st) {
   cudaEventRecord(g_recs.back().b, st);
 }
 
+// ---- FP64 tensor-pipe (DMMA m8n8k4) peak: the roofline denominator of the Legendre kernels -----------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, int iters) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(acc[i][0]), "+d"(acc[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum += acc[i][0] + acc[i][1];
+  if (sum == 123.456) out[0] = sum;   // keep the loop alive
+}
+
 }  // namespace mlegs
 
 using namespace mlegs;
@@ -49,6 +69,39 @@ extern "C" {
 
 int mlegs_b200_prof_enable(int on) {
   g_prof_on = on != 0;
+  return MLEGS_OK;
+}
+
+// Measured DMMA throughput in TFLOP/s (2 flops per FMA): 16 independent accumulator chains per warp, 8 warps per
+// CTA, 4 CTAs per SM, timed with CUDA events on the library's stream (best of 5, ~2.7 ms each).
+int mlegs_b200_dmma_peak(double *tflops) {
+  cudaStream_t st = (cudaStream_t)ctx().stream;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int iters = 8192, blocks = sms * 4;
+  dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);   // warm-up (clocks ramp up over the first milliseconds)
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    double flops = (double)blocks * 8 * iters * 16 * 512.0;   // m8n8k4 = 256 FMA = 512 flops
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    g_launches++;
+  }
+  CUDA_TRY(cudaEventDestroy(e0));
+  CUDA_TRY(cudaEventDestroy(e1));
+  CUDA_TRY(cudaFree(d));
+  *tflops = best;
   return MLEGS_OK;
 }
 

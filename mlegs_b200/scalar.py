@@ -61,6 +61,11 @@ class Scalar:
         check(_lib.lib().mlegs_b200_field_upload(C.byref(self.f), a.ctypes.data_as(C.c_void_p)))
         return self
 
+    def upload_global(self, glb: np.ndarray) -> "Scalar":
+        """disassemble (dist:205-368) without the gather: every rank holds the global array and keeps its slab."""
+        st, sz = self.loc_st, self.loc_sz
+        return self.upload(glb[st[0]:st[0] + sz[0], st[1]:st[1] + sz[1], st[2]:st[2] + sz[2]])
+
     def download(self) -> np.ndarray:
         out = np.empty(self.loc_sz, dtype=np.complex128, order="F")
         check(_lib.lib().mlegs_b200_field_download(C.byref(self.f), out.ctypes.data_as(C.c_void_p)))
@@ -180,6 +185,12 @@ def is_finite(s) -> bool:
 def device_sync(): check(_l().mlegs_b200_device_sync())
 def set_stream(ptr): check(_l().mlegs_b200_set_stream(C.c_void_p(ptr)))
 def launch_count(reset=False) -> int: return int(_l().mlegs_b200_launch_count(int(reset)))
+
+
+def dmma_peak() -> float:
+    v = C.c_double(0.0)
+    check(_l().mlegs_b200_dmma_peak(C.byref(v)))
+    return v.value
 
 
 def prof_enable(on: bool = True): check(_l().mlegs_b200_prof_enable(int(on)))

@@ -38,7 +38,7 @@ def qvort_dist_tp(kit: TfmKit, q: float = 1.0):
             else:
                 acc = acc + (-np.exp(-(rr ** 2.0)) / q / den + 1j * (-np.exp(-(ri ** 2.0)) / q / den))
         glb[:nr, :nph, :nz] = acc[:, :, None]
-        s = Scalar("PPP").upload(glb)
+        s = Scalar("PPP").upload_global(glb)
         ms.trans(s, "FFF")
         ms.idelsqp(s)
         ms.zeroat1(s)
@@ -51,7 +51,7 @@ def uniform_z_fld(kit: TfmKit, b: float = -0.5) -> Scalar:
     p = kit.params
     glb = np.zeros(kit.glb_sz, dtype=np.complex128, order="F")
     glb[: p.nr, : p.np // 2, : p.nz] = complex(b, b)
-    return Scalar("PPP").upload(glb)
+    return Scalar("PPP").upload_global(glb)
 
 
 @dataclass
@@ -127,5 +127,8 @@ def step(st: VortexState, dt: float, check: bool = True):
     ms.zeroat1(st.psi)
     ms.zeroat1(st.chi)
     advection_rhs(st.psi, st.chi, st.nlpsi, st.nlchi, st.uz, st.work)
-    if check and not (ms.is_finite(st.psi) and ms.is_finite(st.chi)):   # check_stability, :397-409
-        raise FloatingPointError("ERROR: non-finite vortex state")
+    if check:   # check_stability, :397-409: allreduce(land) of the per-rank flags
+        from . import dist
+        bad = 0.0 if (ms.is_finite(st.psi) and ms.is_finite(st.chi)) else 1.0
+        if dist.allreduce([bad])[0] > 0.0:
+            raise FloatingPointError("ERROR: non-finite vortex state")
