@@ -54,29 +54,33 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool val
   const int nbytes = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(nbytes) : "memory");
 }
-// DRAM -> L2 prefetch of a contiguous range (bytes: multiple of 16, 16-byte aligned address); no smem involved
-__device__ __forceinline__ void l2_prefetch(const void *gmem, int bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
-}
-#define LEG_PD 3   // chunks of field data kept in flight towards L2 ahead of the cp.async stage
-
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-#define LEG_LDB_F (2 * LEG_KC + 8)       // doubles per kz row of the raw (unfolded) data tiles: conflict-free fragments
+// Per CTA: A (table slice) and the RAW field rows are double-buffered cp.async targets; a cooperative fold pass
+// (each element once per CTA: (f(i) +- f(nr-1-i)) * w(i), 16 FP64 operations per thread and chunk) turns the raw
+// rows of chunk c+1 into the two parity operands F while the tensor pipe works on chunk c.  Keeping the fold out
+// of the fragment path matters: plain FP64 instructions share the pipe with DMMA and would otherwise sit in
+// front of every k-step of every warp.
 struct FwdSmem {
-  double A[2][LEG_MT_F / 2][LEG_LD];     // [parity][row within parity][k]
-  double T[LEG_NTC][LEG_LDB_F];          // raw top rows    f(i, kz), i = chunk rows, (re, im) interleaved
-  double Bm[LEG_NTC][LEG_LDB_F];         // raw mirror rows f(nr-1-i, kz)
-  double W[LEG_KC];                      // quadrature weights of the chunk rows
+  double A[2][2][LEG_MT_F / 2][LEG_LD];     // [buf][parity][row within parity][k]
+  double F[2][2][2 * LEG_NTC][LEG_LD];      // [buf][fold: 0 sum, 1 difference][real column][k]
+  cplx T[2][LEG_NTC][LEG_KC];               // [buf] raw top rows    f(i, kz)
+  cplx Bm[2][LEG_NTC][LEG_KC];              // [buf] raw mirror rows f(nr-1-i, kz)
+  double W[2][LEG_KC];                      // [buf] quadrature weights of the chunk rows
+};
+
+template <int NACT>
+struct IntC {
+  static constexpr int value = NACT;
 };
 
 __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  FwdSmem *sm = reinterpret_cast<FwdSmem *>(smraw);
+  FwdSmem &S = *reinterpret_cast<FwdSmem *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int par = warp >> 2, wr = (warp >> 1) & 1, wc = warp & 1;
   const int ml = blockIdx.z;
@@ -101,20 +105,18 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   const bool active = (n0 < nn);
   const int nchunks = active ? (a.nrh + LEG_KC - 1) / LEG_KC : 0;
 
-  // Stage chunk c (rows i = c*KC .. +KC of the half grid) into buffer `buf`; out-of-range pieces are zero-filled.
-  auto issue = [&](int c, int buf) {
-    FwdSmem &S = sm[buf];
+  // table rows of chunk c -> A[buf]; out-of-range pieces are zero-filled
+  auto issue_A = [&](int c, int buf) {
     const int i0 = c * LEG_KC;
-    // A: 128 table rows x KC doubles
     if (vec2) {
-      // 128 x 8 16-byte pieces -> 4 per thread
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4; ++j) {          // 128 rows x 8 16-byte pieces
         const int p = tid + LEG_THREADS * j;
         const int r = p >> 3, k2 = (p & 7) * 2;
         const int n = n0 + r;
         const bool ok = (n < nn) && (i0 + k2 < a.nrh);
-        cp_async16(&S.A[r & 1][r >> 1][k2], ok ? (const void *)&pf[(size_t)n * a.nrh + i0 + k2] : (const void *)pf, ok);
+        cp_async16(&S.A[buf][r & 1][r >> 1][k2], ok ? (const void *)&pf[(size_t)n * a.nrh + i0 + k2] : (const void *)pf,
+                   ok);
       }
     } else {
 #pragma unroll
@@ -123,10 +125,13 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
         const int r = p >> 4, k = p & 15;
         const int n = n0 + r;
         const bool ok = (n < nn) && (i0 + k < a.nrh);
-        cp_async8(&S.A[r & 1][r >> 1][k], ok ? (const void *)&pf[(size_t)n * a.nrh + i0 + k] : (const void *)pf, ok);
+        cp_async8(&S.A[buf][r & 1][r >> 1][k], ok ? (const void *)&pf[(size_t)n * a.nrh + i0 + k] : (const void *)pf, ok);
       }
     }
-    // raw data: 32 kz x KC complex, top and mirrored rows -> 2 + 2 per thread
+  };
+  // raw field rows (top and mirror) + weights of chunk c -> T/Bm/W[buf]
+  auto issue_raw = [&](int c, int buf) {
+    const int i0 = c * LEG_KC;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int p = tid + LEG_THREADS * j;
@@ -134,87 +139,92 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
       const int kz = kz0 + kzl, i = i0 + k;
       const bool ok = (kz < a.nzl) && (i < a.nrh);
       const cplx *col = in + (size_t)kz * col_stride;
-      cp_async16(&S.T[kzl][2 * k], ok ? (const void *)&col[i] : (const void *)in, ok);
-      cp_async16(&S.Bm[kzl][2 * k], ok ? (const void *)&col[a.nr - 1 - i] : (const void *)in, ok);
+      cp_async16(&S.T[buf][kzl][k], ok ? (const void *)&col[i] : (const void *)in, ok);
+      cp_async16(&S.Bm[buf][kzl][k], ok ? (const void *)&col[a.nr - 1 - i] : (const void *)in, ok);
     }
     if (have_w && tid < LEG_KC) {
       const bool ok = i0 + tid < a.nrh;
-      cp_async8(&S.W[tid], ok ? (const void *)&a.w[i0 + tid] : (const void *)a.w, ok);
+      cp_async8(&S.W[buf][tid], ok ? (const void *)&a.w[i0 + tid] : (const void *)a.w, ok);
     }
   };
-
-  // The field columns of this CTA are streamed exactly once and come from DRAM in 256-byte pieces: keep LEG_PD
-  // chunks of them on their way into L2 so that the cp.async stage only ever sees L2 latency.
-  auto prefetch = [&](int c) {
-    if (tid < 2 * LEG_NTC) {
-      const int kz = kz0 + (tid & (LEG_NTC - 1)), i0 = c * LEG_KC;
-      if (c < nchunks && kz < a.nzl && i0 < a.nrh) {
-        const int cnt = min(LEG_KC, a.nrh - i0);
-        const cplx *col = in + (size_t)kz * col_stride;
-        l2_prefetch((tid >> 5) ? (const void *)&col[a.nr - i0 - cnt] : (const void *)&col[i0], cnt * 16);
+  // fold raw chunk c (in T/Bm/W[rbuf]) into the parity operands F[fbuf]; thread -> (k = tid & 15, kz = tid>>4 + 16 j)
+  auto fold = [&](int c, int rbuf, int fbuf) {
+    const int k = tid & 15;
+    const double wk = have_w ? S.W[rbuf][k] : 1.0;
+    double l1 = 0.0, l2 = 0.0;
+    if (use_ln) {   // log term removed from the real part of the m = 0 column (ops:193-195)
+      const int i = c * LEG_KC + k;
+      if (i < a.nrh) {
+        l1 = a.lnval * __ldg(&a.lnx[i]);
+        l2 = a.lnval * __ldg(&a.lnx[a.nr - 1 - i]);
       }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kzl = (tid >> 4) + 16 * j;
+      cplx t = S.T[rbuf][kzl][k], b = S.Bm[rbuf][kzl][k];
+      t.x -= l1;
+      b.x -= l2;
+      S.F[fbuf][0][2 * kzl][k] = (t.x + b.x) * wk;
+      S.F[fbuf][0][2 * kzl + 1][k] = (t.y + b.y) * wk;
+      S.F[fbuf][1][2 * kzl][k] = (t.x - b.x) * wk;
+      S.F[fbuf][1][2 * kzl + 1][k] = (t.y - b.y) * wk;
     }
   };
 
   const int fr = lane >> 2, fk = lane & 3;
-  // The warp's four 8-row tiles are interleaved with the other row-warp's (tile index 2 mt + wr), and tiles
-  // that lie entirely beyond the truncation nn(m) are skipped: both row-warps (hence all four SM sub-partitions)
-  // keep the same number of DMMAs when nn is not a multiple of the 128-row CTA tile.
+  // The warp's four 8-row tiles are interleaved with the other row-warp's (tile index 2 mt + wr); tiles entirely
+  // beyond the truncation nn(m) are skipped by compiling the main loop for each possible count (a predicated-off
+  // DMMA still occupies the pipe).
   int nact = 0;
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) nact += (n0 + 2 * ((2 * mt + wr) * 8) + par < nn) ? 1 : 0;
-  const bool minus = (par ^ a.swap_parity) != 0;        // fold sign: even rows take f(i) + f(mirror), odd rows the difference
-  const int bre = fr & 1;                               // this lane's real column is the re (0) or im (1) part
+  const int fsel = par ^ a.swap_parity;                 // even rows contract with the sum fold, odd rows with the difference
+
+  auto mainloop = [&](auto nact_c) {
+    constexpr int NACT = decltype(nact_c)::value;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      cp_async_wait_all();
+      __syncthreads();     // A(c), raw(c+1) have landed; F(c) is complete; everyone has left iteration c-1
+      if (c + 1 < nchunks) issue_A(c + 1, buf ^ 1);
+      if (c + 2 < nchunks) issue_raw(c + 2, buf);
+      cp_async_commit();
+      if (c + 1 < nchunks) fold(c + 1, buf ^ 1, buf ^ 1);
+#pragma unroll
+      for (int ks = 0; ks < LEG_KC / 4; ++ks) {
+        const int k = ks * 4 + fk;
+        double af[4], bf[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+          if (mt < NACT) af[mt] = S.A[buf][par][(2 * mt + wr) * 8 + fr][k];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bf[nt] = S.F[buf][fsel][wc * 32 + nt * 8 + fr][k];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+          if (mt < NACT) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+          }
+      }
+    }
+  };
 
   if (nchunks > 0) {
-    issue(0, 0);
+    issue_A(0, 0);
+    issue_raw(0, 0);
     cp_async_commit();
-#pragma unroll
-    for (int d = 1; d <= LEG_PD; ++d) prefetch(d);
-  }
-  for (int c = 0; c < nchunks; ++c) {
-    const int buf = c & 1;
     cp_async_wait_all();
-    __syncthreads();            // chunk c has landed for everyone; everyone is done reading buffer buf^1
-    if (c + 1 < nchunks) {
-      issue(c + 1, buf ^ 1);
-      cp_async_commit();
-      prefetch(c + 1 + LEG_PD);
-    }
-    const FwdSmem &S = sm[buf];
-#pragma unroll
-    for (int ks = 0; ks < LEG_KC / 4; ++ks) {
-      const int k = ks * 4 + fk;
-      double af[4], bf[4];
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) af[mt] = S.A[par][(2 * mt + wr) * 8 + fr][k];
-      double wk = have_w ? S.W[k] : 1.0;
-      double l1 = 0.0, l2 = 0.0;
-      if (use_ln && bre == 0) {   // log term removed from the real part of the m = 0 column (ops:193-195)
-        const int i = c * LEG_KC + k;
-        if (i < a.nrh) {
-          l1 = a.lnval * __ldg(&a.lnx[i]);
-          l2 = a.lnval * __ldg(&a.lnx[a.nr - 1 - i]);
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int kzl = (wc * 32 + nt * 8 + fr) >> 1;
-        double t = S.T[kzl][2 * k + bre];
-        double b = S.Bm[kzl][2 * k + bre];
-        if (use_ln) {
-          t -= l1;
-          b -= l2;
-        }
-        double f = minus ? (t - b) : (t + b);
-        bf[nt] = have_w ? f * wk : f;
-      }
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-        if (mt < nact) {
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-        }
+    __syncthreads();
+    if (nchunks > 1) issue_raw(1, 1);
+    cp_async_commit();
+    fold(0, 0, 0);
+    switch (nact) {
+      case 4: mainloop(IntC<4>{}); break;
+      case 3: mainloop(IntC<3>{}); break;
+      case 2: mainloop(IntC<2>{}); break;
+      case 1: mainloop(IntC<1>{}); break;
+      default: mainloop(IntC<0>{}); break;
     }
   }
 
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   // 16-byte-per-lane rows (n fastest), 2 KB per kz column.
   __syncthreads();            // everyone is done with the staging buffers
   cplx(*cs)[LEG_MT_F + 2] = reinterpret_cast<cplx(*)[LEG_MT_F + 2]>(smraw);
-  static_assert(sizeof(cplx) * LEG_NTC * (LEG_MT_F + 2) <= 2 * sizeof(FwdSmem), "epilogue smem");
+  static_assert(sizeof(cplx) * LEG_NTC * (LEG_MT_F + 2) <= sizeof(FwdSmem), "epilogue smem");
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     const int nl = 2 * ((2 * mt + wr) * 8 + fr) + par;
@@ -313,22 +323,11 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
     }
   };
 
-  auto prefetch = [&](int c) {   // DRAM -> L2 for the coefficient columns, LEG_PD chunks ahead (512-byte pieces)
-    if (tid < LEG_NTC) {
-      const int kz = kz0 + tid, nb = c * 2 * LEG_KC;
-      if (c < nchunks && kz < a.nzl && nb < nn) {
-        const int cnt = min(2 * LEG_KC, nn - nb);
-        l2_prefetch(&in[(size_t)kz * col_stride + nb], cnt * 16);
-      }
-    }
-  };
   const int fr = lane >> 2, fk = lane & 3;
   const int bre = fr & 1;
   if (nchunks > 0) {
     issue(0, 0);
     cp_async_commit();
-#pragma unroll
-    for (int d = 1; d <= LEG_PD; ++d) prefetch(d);
   }
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
@@ -337,7 +336,6 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
     if (c + 1 < nchunks) {
       issue(c + 1, buf ^ 1);
       cp_async_commit();
-      prefetch(c + 1 + LEG_PD);
     }
     const BwdSmem &S = sm[buf];
 #pragma unroll
@@ -400,7 +398,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
 
 int setup_leg_kernels() {
   CUDA_TRY(cudaFuncSetAttribute(leg_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(2 * sizeof(FwdSmem))));
+                                (int)sizeof(FwdSmem)));
   CUDA_TRY(cudaFuncSetAttribute(leg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(2 * sizeof(BwdSmem))));
   return MLEGS_OK;
@@ -410,7 +408,7 @@ int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrdim + LEG_MT_F - 1) / LEG_MT_F, a.npl);
   prof_begin("legendre_forward", st);
-  leg_forward_kernel<<<grid, LEG_THREADS, 2 * sizeof(FwdSmem), st>>>(a);
+  leg_forward_kernel<<<grid, LEG_THREADS, sizeof(FwdSmem), st>>>(a);
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
