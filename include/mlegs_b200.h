@@ -133,6 +133,12 @@ int mlegs_b200_ihelm(mlegs_field *s, double alpha);                       /* ops
 int mlegs_b200_helmp(mlegs_field *s, int power, double alpha, double beta);   /* ops:856-903 */
 int mlegs_b200_ihelmp(mlegs_field *s, int power, double alpha, double beta);  /* ops:905-1000 */
 
+/* The LU factors of the (m,k) band systems depend on the operator only (power, alpha, beta, truncation), not on
+ * the right-hand side: by default they are kept in HBM after the first solve and later solves run the two
+ * substitutions only (bit-identical results; the reference re-factors in every call, ops:953-984).  on = 0
+ * restores factor-per-call and frees the cache. */
+int mlegs_b200_solve_cache(int on);
+
 /* ---- time integrators ---------------------------------------------------------------- */
 int mlegs_b200_fefe(mlegs_field *s, const mlegs_field *nl, double dt);    /* ops:1065-1094 */
 int mlegs_b200_febe(mlegs_field *s, const mlegs_field *nl, double dt);    /* ops:1157-1198 */

@@ -82,6 +82,7 @@ _SIGS = {
     "mlegs_b200_ihelm": (C.c_int, [_P(Field), C.c_double]),
     "mlegs_b200_helmp": (C.c_int, [_P(Field), C.c_int, C.c_double, C.c_double]),
     "mlegs_b200_ihelmp": (C.c_int, [_P(Field), C.c_int, C.c_double, C.c_double]),
+    "mlegs_b200_solve_cache": (C.c_int, [C.c_int]),
     "mlegs_b200_fefe": (C.c_int, [_P(Field), _P(Field), C.c_double]),
     "mlegs_b200_febe": (C.c_int, [_P(Field), _P(Field), C.c_double]),
     "mlegs_b200_abcn": (C.c_int, [_P(Field)] * 4 + [C.c_double]),

@@ -8,7 +8,9 @@
 // the -k^2 shift is applied on the fly.  Compiled with -fmad=false: products and sums round separately,
 // in the reference's order, so matrices are bit-identical to a non-fused CPU evaluation.
 #include <cmath>
+#include <cstring>
 #include <thread>
+#include <vector>
 
 #include "kernels.h"
 
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
     double *AB = Pa + (a.power > 2 ? 17 * a.nnmax : 0);
     double *Pb = AB;
     double *rhs = AB + (size_t)ldab * a.nnmax;
+    int *piv = reinterpret_cast<int *>(rhs + 2 * a.nnmax);
     cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
     const double *tab = a.tab + (size_t)mglob * 5 * a.ne;
     const double akv = a.ak[k];
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
       double pv = (lane <= km) ? fabs(cj[kv + lane]) : -1.0;
       int jp = lane;
       warp_argmax_first(pv, jp);
+      if (lane == 0) piv[jj] = (pv != 0.0) ? jp : 0;
       if (pv != 0.0) {
         ju = max(ju, min(jj + ku + jp, nn - 1));
         const int ncol = ju - jj + 1;
@@ -422,6 +426,14 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
         atomicOr(a.flag + 1, 1);   // 'lurc: lu factorization resulted in failure'
       }
     }
+    if (a.fac_ab) {
+      // keep the factors: every later solve with this operator only runs the two substitutions
+      __syncwarp();
+      const long long c0 = a.fac_off[j] + (long long)(k - a.k0) * nn;   // first column of this system
+      double *fa = a.fac_ab + c0 * ldab;
+      for (int idx = lane; idx < ldab * nn; idx += 32) fa[idx] = AB[idx];
+      for (int idx = lane; idx < nn; idx += 32) a.fac_piv[c0 + idx] = (unsigned char)piv[idx];
+    }
     // ---- ztbsv: upper, no transpose, non-unit, bandwidth kv ----
     for (int jj = nn - 1; jj >= 0; --jj) {
       const double *cj = AB + (size_t)jj * ldab;
@@ -450,17 +462,232 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// solves with cached factors: zgbtrs only (forward sweep with the stored multipliers and pivots, then ztbsv),
+// the same operations in the same order as the factor-and-solve kernel above, so results are bit-identical.
+// One warp per (m,k) system; the right-hand side lives in shared memory, the factors stream from HBM exactly
+// once per solve (they are the only traffic that matters: ldab*8 bytes per row against 16 bytes of field data).
+// ---------------------------------------------------------------------------------------------
+#define CSOLVE_WARPS 8
+
+__global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(SolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nsys = a.npl * a.nk;
+  const int kl = a.kl, ku = a.ku, kv = kl + ku, ldab = 2 * kl + ku + 1;
+  double *rhs = reinterpret_cast<double *>(smraw) + (size_t)warp * 2 * a.nnmax;
+  for (int sys = blockIdx.x * CSOLVE_WARPS + warp; sys < nsys; sys += gridDim.x * CSOLVE_WARPS) {
+    // consecutive systems of a block share the column j (same nn, neighbouring factor storage)
+    const int j = sys / a.nk;
+    const int k = a.k0 + sys % a.nk;
+    const int mglob = a.m0 + j;
+    const int nn = nn_of(mglob, a.nrc, a.npc);
+    if (nn < 1) continue;
+    cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+    const bool special = (a.special00 && mglob == 0 && k == 0);
+    const long long c0 = a.fac_off[j] + (long long)(k - a.k0) * nn;
+    const double *__restrict__ AB = a.fac_ab + c0 * ldab;
+    const unsigned char *__restrict__ piv = a.fac_piv + c0;
+    for (int i = lane; i < nn; i += 32) {
+      cplx v;
+      if (special && a.special00 == 2)
+        v = (i == 0) ? make_double2(a.preln_rhs, 0.0) : col[i - 1];
+      else
+        v = col[i];
+      rhs[2 * i] = v.x;
+      rhs[2 * i + 1] = v.y;
+    }
+    __syncwarp();
+    // ---- forward sweep (zgbtrs, external/lapack/SRC/zgbtrs.f:205-232) ----
+    // multipliers of 4 columns per load: lane = 8 u + i holds L(i+1) of column jj0+u (kl <= 8)
+    for (int jj0 = 0; jj0 < nn; jj0 += 4) {
+      const int u_ld = lane >> 3, i_ld = lane & 7;
+      double lreg = 0.0;
+      if (jj0 + u_ld < nn && i_ld < kl) lreg = __ldg(&AB[(size_t)(jj0 + u_ld) * ldab + kv + 1 + i_ld]);
+      int preg = (lane < 4 && jj0 + lane < nn) ? (int)__ldg(&piv[jj0 + lane]) : 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = jj0 + u;
+        if (jj >= nn) break;
+        const int km = min(kl, nn - 1 - jj);
+        const int jp = __shfl_sync(0xffffffffu, preg, u);
+        const double l = __shfl_sync(0xffffffffu, lreg, 8 * u + ((lane - 1) & 7));   // lane i (1..km) gets L(i)
+        if (jp != 0) {
+          if (lane == 0) {
+            double tr = rhs[2 * (jj + jp)], ti = rhs[2 * (jj + jp) + 1];
+            rhs[2 * (jj + jp)] = rhs[2 * jj];
+            rhs[2 * (jj + jp) + 1] = rhs[2 * jj + 1];
+            rhs[2 * jj] = tr;
+            rhs[2 * jj + 1] = ti;
+          }
+          __syncwarp();
+        }
+        if (km > 0) {
+          if (lane >= 1 && lane <= km) {
+            double tr = -rhs[2 * jj], ti = -rhs[2 * jj + 1];
+            rhs[2 * (jj + lane)] = rhs[2 * (jj + lane)] + l * tr;
+            rhs[2 * (jj + lane) + 1] = rhs[2 * (jj + lane) + 1] + l * ti;
+          }
+          __syncwarp();
+        }
+      }
+    }
+    // ---- ztbsv: upper, no transpose, non-unit, bandwidth kv ----
+    // U column of step jj: lane t holds U(jj - t, jj) = AB[kv - t], prefetched one step ahead
+    double unext = (lane <= kv && nn - 1 - lane >= 0) ? __ldg(&AB[(size_t)(nn - 1) * ldab + kv - lane]) : 0.0;
+    for (int jj = nn - 1; jj >= 0; --jj) {
+      const double u = unext;
+      if (jj > 0 && lane <= kv && lane <= jj - 1) unext = __ldg(&AB[(size_t)(jj - 1) * ldab + kv - lane]);
+      double xr = rhs[2 * jj], xi = rhs[2 * jj + 1];
+      if (xr != 0.0 || xi != 0.0) {
+        const double ujj = __shfl_sync(0xffffffffu, u, 0);
+        xr = xr / ujj;
+        xi = xi / ujj;
+        __syncwarp();
+        if (lane == 0) {
+          rhs[2 * jj] = xr;
+          rhs[2 * jj + 1] = xi;
+        }
+        const int cnt = min(jj, kv);
+        if (lane >= 1 && lane <= cnt) {
+          int i = jj - lane;
+          rhs[2 * i] = rhs[2 * i] - xr * u;
+          rhs[2 * i + 1] = rhs[2 * i + 1] - xi * u;
+        }
+      } else {
+        __shfl_sync(0xffffffffu, u, 0);
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < nn; i += 32) col[i] = make_double2(rhs[2 * i], rhs[2 * i + 1]);
+    __syncwarp();
+  }
+}
+
+// ---- factor cache ---------------------------------------------------------------------------------------------
+struct FactorEntry {
+  SolveArgs key;            // operator identity (pointer fields zeroed)
+  double *ab = nullptr;
+  unsigned char *piv = nullptr;
+  long long *off = nullptr;
+  size_t bytes = 0;
+  unsigned long long stamp = 0;
+};
+static std::vector<FactorEntry> g_fcache;
+static unsigned long long g_fstamp = 0;
+static int g_fcache_on = 1;
+
+static void free_entry(FactorEntry &e) {
+  if (e.ab) cudaFree(e.ab);
+  if (e.piv) cudaFree(e.piv);
+  if (e.off) cudaFree(e.off);
+  e = FactorEntry();
+}
+void band_solve_cache_clear() {
+  for (auto &e : g_fcache) free_entry(e);
+  g_fcache.clear();
+}
+void band_solve_cache_enable(int on) {
+  g_fcache_on = on;
+  if (!on) band_solve_cache_clear();
+}
+
+static SolveArgs key_of(const SolveArgs &a) {
+  SolveArgs k;
+  memset(&k, 0, sizeof(k));   // padding bytes too: keys are compared with memcmp
+  k.nrl = a.nrl; k.npl = a.npl; k.m0 = a.m0; k.k0 = a.k0; k.nk = a.nk; k.ne = a.ne;
+  k.nrc = a.nrc; k.npc = a.npc; k.nnmax = a.nnmax; k.kl = a.kl; k.ku = a.ku; k.power = a.power;
+  k.add_alpha = a.add_alpha; k.alpha = a.alpha; k.beta = a.beta; k.special00 = a.special00;
+  k.sp0 = a.sp0; k.sp1 = a.sp1; k.sp2 = a.sp2;   // preln_rhs only enters the right-hand side
+  return k;
+}
+
 int launch_band_solve(SolveArgs a, cudaStream_t st) {
   Context &c = ctx();
   if (a.npl <= 0 || a.nk <= 0) return MLEGS_OK;
   const int ldab = 2 * a.kl + a.ku + 1;
-  a.ws_doubles = (size_t)(5 + (a.power > 2 ? 17 : 0) + ldab + 2) * a.nnmax;
+  a.flag = c.d_flag;
+  a.fac_ab = nullptr;
+  a.fac_piv = nullptr;
+  a.fac_off = nullptr;
+
+  // ---- cached factors? ----
+  FactorEntry *hit = nullptr;
+  SolveArgs key = key_of(a);
+  if (g_fcache_on) {
+    for (auto &e : g_fcache)
+      if (memcmp(&e.key, &key, sizeof(SolveArgs)) == 0) hit = &e;
+  }
+  if (hit) {
+    hit->stamp = ++g_fstamp;
+    a.fac_ab = hit->ab;
+    a.fac_piv = hit->piv;
+    a.fac_off = hit->off;
+    const int nsys = a.npl * a.nk;
+    size_t smem = (size_t)CSOLVE_WARPS * 2 * a.nnmax * sizeof(double);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = smem;
+    }
+    int blocks = (nsys + CSOLVE_WARPS - 1) / CSOLVE_WARPS;
+    prof_begin(a.power > 2 ? "ihelmp_solve_cached" : "band_solve_cached", st);
+    band_solve_cached_kernel<<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
+    prof_end(st);
+    KERNEL_CHECK();
+    return MLEGS_OK;
+  }
+
+  // ---- first solve with this operator: factor (and keep the factors if memory allows) ----
+  if (g_fcache_on && a.kl <= 8) {
+    std::vector<long long> off(a.npl + 1, 0);
+    for (int j = 0; j < a.npl; ++j) {
+      int m = a.m0 + j;
+      int nn = (m < a.npc) ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
+      off[j + 1] = off[j] + (long long)nn * a.nk;
+    }
+    const size_t ncols = (size_t)off[a.npl];
+    const size_t need = ncols * ldab * sizeof(double) + ncols + off.size() * sizeof(long long);
+    size_t freeb = 0, totalb = 0;
+    cudaMemGetInfo(&freeb, &totalb);
+    // evict least recently used entries until the new one fits in half of the free memory
+    while (!g_fcache.empty() && need > freeb / 2) {
+      size_t lru = 0;
+      for (size_t i = 1; i < g_fcache.size(); ++i)
+        if (g_fcache[i].stamp < g_fcache[lru].stamp) lru = i;
+      CUDA_TRY(cudaStreamSynchronize(st));
+      free_entry(g_fcache[lru]);
+      g_fcache.erase(g_fcache.begin() + lru);
+      cudaMemGetInfo(&freeb, &totalb);
+    }
+    if (ncols > 0 && need <= freeb / 2) {
+      FactorEntry e;
+      e.key = key;
+      e.bytes = need;
+      e.stamp = ++g_fstamp;
+      bool ok = cudaMalloc((void **)&e.ab, ncols * ldab * sizeof(double)) == cudaSuccess &&
+                cudaMalloc((void **)&e.piv, ncols) == cudaSuccess &&
+                cudaMalloc((void **)&e.off, off.size() * sizeof(long long)) == cudaSuccess;
+      if (ok) {
+        CUDA_TRY(cudaMemcpyAsync(e.off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // `off` goes out of scope
+        g_fcache.push_back(e);
+        a.fac_ab = e.ab;
+        a.fac_piv = e.piv;
+        a.fac_off = e.off;
+      } else {
+        cudaGetLastError();
+        free_entry(e);
+      }
+    }
+  }
+
+  a.ws_doubles = (size_t)(5 + (a.power > 2 ? 17 : 0) + ldab + 2) * a.nnmax + (a.nnmax + 1) / 2;   // + pivots (ints)
   // Pb (used from power 6 on) aliases AB and holds at most 13 bands stored with offset 8 -> 15 nn doubles
   if (a.power > 4 && ldab < 15) return fail(MLEGS_E_ARG, "band_solve: internal workspace aliasing violated");
   size_t smem = a.ws_doubles * sizeof(double) * SOLVE_WARPS;
   const int nsys = a.npl * a.nk;
   int blocks = (nsys + SOLVE_WARPS - 1) / SOLVE_WARPS;
-  a.flag = c.d_flag;
   if (smem <= 200 * 1024) {
     a.ws_global = nullptr;
     static size_t attr_set = 0;

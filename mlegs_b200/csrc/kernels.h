@@ -154,7 +154,14 @@ struct SolveArgs {
   size_t ws_doubles;
   double *ws_global;
   int *flag;
+  // factor cache (filled on the first solve with a given operator, reused by every later right-hand side)
+  double *fac_ab;                // LAPACK band storage of the LU factors, all systems
+  unsigned char *fac_piv;        // pivot offsets jp (0..kl) per column
+  const long long *fac_off;      // per local column j: offset (in columns) of system (j, k0); see launch_band_solve
 };
 int launch_band_solve(SolveArgs a, cudaStream_t st);
+void band_solve_cache_clear();
+// 1: solves reuse cached LU factors (default); 0: every call factors again (the reference's behaviour)
+void band_solve_cache_enable(int on);
 
 }  // namespace mlegs

@@ -829,6 +829,11 @@ int mlegs_b200_helmp(mlegs_field *s, int power, double alpha, double beta) { ret
 int mlegs_b200_ihelmp(mlegs_field *s, int power, double alpha, double beta) {
   return ihelmp_impl(s, power, alpha, beta);
 }
+int mlegs_b200_solve_cache(int on) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  band_solve_cache_enable(on);
+  return MLEGS_OK;
+}
 int mlegs_b200_fefe(mlegs_field *s, const mlegs_field *nl, double dt) { return fefe_impl(s, nl, dt); }
 int mlegs_b200_febe(mlegs_field *s, const mlegs_field *nl, double dt) { return febe_impl(s, nl, dt); }
 int mlegs_b200_abcn(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl_p, double dt) {

@@ -148,6 +148,7 @@ def idel2(s, preln=None):
 def ihelm(s, alpha): check(_l().mlegs_b200_ihelm(C.byref(s.f), alpha))
 def helmp(s, power, alpha, beta): check(_l().mlegs_b200_helmp(C.byref(s.f), power, alpha, beta))
 def ihelmp(s, power, alpha, beta): check(_l().mlegs_b200_ihelmp(C.byref(s.f), power, alpha, beta))
+def solve_cache(on: bool): check(_l().mlegs_b200_solve_cache(int(on)))
 def fefe(s, nl, dt): check(_l().mlegs_b200_fefe(C.byref(s.f), C.byref(nl.f), dt))
 def febe(s, nl, dt): check(_l().mlegs_b200_febe(C.byref(s.f), C.byref(nl.f), dt))
 

@@ -161,6 +161,33 @@ def test_ihelm_and_idel2(case):
         mb.ihelm(s, 0.0)
 
 
+@pytest.mark.parametrize("case", ["gate3d", "chopped"])
+def test_cached_factors_are_bit_identical(case):
+    """Solves that reuse the cached LU factors run the same operations in the same order as factor-and-solve."""
+    kit, ok = _setup(case)
+    hp = CASES[case][7]
+    rhs = [random_fff(ok, seed=s) for s in (21, 22)]
+
+    def run_all():
+        out = []
+        for e in rhs:
+            for fn in (lambda s: mb.ihelmp(s, hp, -4.0e7, 200.0), lambda s: mb.ihelm(s, -321.0), lambda s: mb.idel2(s),
+                       lambda s: mb.idel2(s, preln=0.4)):
+                s = mb.Scalar("FFF").upload(e)
+                fn(s)
+                out.append((s.download(), s.ln))
+        return out
+
+    mb.solve_cache(False)
+    ref = run_all()                 # every call factors (the reference's behaviour)
+    mb.solve_cache(True)
+    first = run_all()               # rhs 0 fills the cache, rhs 1 hits it
+    second = run_all()              # everything hits
+    for a, b, c in zip(ref, first, second):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[0], c[0])
+        assert a[1] == b[1] == c[1]
+
+
 def test_idel2_inverts_del2():
     # apps/inverse_laplacian.f90
     kit, ok = _setup("gate2d")
