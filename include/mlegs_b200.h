@@ -111,6 +111,9 @@ int mlegs_b200_host_unregister(void *host_ptr);
 int mlegs_b200_trans(mlegs_field *s, const char to[3]);                   /* ops:157-235 */
 /* Reference-facing call on a HOST array (the Fortran s%e): H2D, trans, D2H. */
 int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], double ln);
+/* The same for n independent host arrays (a caller that transforms several scalars back to back, e.g. the three
+ * components in ops:1503-1505): copies and transforms are pipelined over PCIe in both directions.  ln may be NULL. */
+int mlegs_b200_trans_host_batch(int n, void *const *host_e, const char from[3], const char to[3], const double *ln);
 /* scalar_exchange, dist:6-67 (slab layout: only (2,1)/(1,2) move data) */
 int mlegs_b200_exchange(mlegs_field *s, int axis_old, int axis_new);
 

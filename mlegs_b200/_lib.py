@@ -66,6 +66,7 @@ _SIGS = {
     "mlegs_b200_host_unregister": (C.c_int, [C.c_void_p]),
     "mlegs_b200_trans": (C.c_int, [_P(Field), C.c_char_p]),
     "mlegs_b200_trans_host": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]),
+    "mlegs_b200_trans_host_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p]),
     "mlegs_b200_exchange": (C.c_int, [_P(Field), C.c_int, C.c_int]),
     "mlegs_b200_chop": (C.c_int, [_P(Field)]),
     "mlegs_b200_dealias": (C.c_int, [_P(Field)]),

@@ -16,91 +16,11 @@
 // bit-identical results.
 #include <cstring>
 
-#include "kernels.h"
+#include "dist_dev.cuh"
 
 namespace mlegs {
 
-#define DIST_MAX_RANKS 16
-#define DIST_FLAG_BYTES 4096
-#define DIST_RED_DOUBLES 16384                      // per rank and parity (>= 2 nz)
-#define DIST_SPIN_LIMIT (1ll << 31)                 // ~1-2 s of clock64 ticks before giving up
-
-struct WinHeader {                                  // lives at the start of every window
-  unsigned long long arrive[DIST_MAX_RANKS];        // data barrier: epoch published by rank q
-  unsigned long long red_arrive[DIST_MAX_RANKS];    // reduction barrier
-};
-
-static size_t win_red_offset() { return DIST_FLAG_BYTES; }
-static size_t win_data_offset() {
-  return DIST_FLAG_BYTES + (size_t)2 * DIST_MAX_RANKS * DIST_RED_DOUBLES * sizeof(double);
-}
-static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-
-struct DistState {
-  bool attached = false;
-  void *base[DIST_MAX_RANKS] = {nullptr};           // window base of every rank as mapped here
-  unsigned long long epoch = 0, red_epoch = 0;
-  unsigned int *d_ctr = nullptr;                    // local CTA counter (last-block detection)
-  size_t wstride = 0;                               // bytes of one W buffer
-};
 static DistState g_dist;
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.global.release.sys.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.global.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Destination of local element (i, j, k) of rank `me` in an exchange: owning rank q and linear index inside
-// q's new local block.  Shared by the put kernel and the host-side plan (mlegs_b200_dist_put_map), which the
-// CPU tests check against the reference's subarray semantics (dist:395-504).
-// dir 0: (2,1) exchange, src (r_loc, npdim, nz) -> (nrdim, m_cnt[q], nz);  dir 1: (1,2), src (nrdim, m_loc, nz)
-// -> (r_cnt[q], npdim, nz).
-__host__ __device__ inline void slab_put_index(int dir, int me, int nranks, const int *r_cnt, const int *r_off,
-                                               const int *m_cnt, const int *m_off, int nrdim, int npdim, int i, int j,
-                                               int k, int *q_out, size_t *dst_out) {
-  int q = 0;
-  if (dir == 0) {
-    while (q + 1 < nranks && j >= m_off[q + 1]) ++q;
-    *dst_out = ((size_t)k * m_cnt[q] + (j - m_off[q])) * nrdim + r_off[me] + i;
-  } else {
-    while (q + 1 < nranks && i >= r_off[q + 1]) ++q;
-    *dst_out = ((size_t)k * npdim + m_off[me] + j) * r_cnt[q] + (i - r_off[q]);
-  }
-  *q_out = q;
-}
-
-struct PeerTable {
-  void *base[DIST_MAX_RANKS];
-  int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
-  int rank, nranks;
-  size_t data_off;      // byte offset of W[parity] inside a window
-  unsigned long long epoch;
-  unsigned int *ctr;
-  int *flag;            // device error flags ([2] = exchange timeout)
-};
-
-// publish `epoch` to all peers and wait for theirs; called by one thread of the last CTA
-__device__ void barrier_publish_wait(const PeerTable &t, bool reduction) {
-  for (int q = 0; q < t.nranks; ++q) {
-    WinHeader *h = reinterpret_cast<WinHeader *>(t.base[q]);
-    st_release_sys(reduction ? &h->red_arrive[t.rank] : &h->arrive[t.rank], t.epoch);
-  }
-  WinHeader *me = reinterpret_cast<WinHeader *>(t.base[t.rank]);
-  for (int q = 0; q < t.nranks; ++q) {
-    const unsigned long long *p = reduction ? &me->red_arrive[q] : &me->arrive[q];
-    const long long t0 = clock64();
-    while (ld_acquire_sys(p) < t.epoch) {
-      if (clock64() - t0 > DIST_SPIN_LIMIT) {
-        atomicOr(t.flag + 2, 1);
-        break;
-      }
-    }
-  }
-}
 
 // dir 0: (2,1) exchange, src (r_loc, npdim, nz) -> peers' (nrdim, m_cnt[q], nz)   [phi local -> r local]
 // dir 1: (1,2) exchange, src (nrdim, m_loc, nz) -> peers' (r_cnt[q], npdim, nz)   [r local -> phi local]
@@ -121,17 +41,7 @@ __global__ void __launch_bounds__(256) exchange_put_kernel(PeerTable t, const cp
     cplx *w = reinterpret_cast<cplx *>(reinterpret_cast<char *>(t.base[q]) + t.data_off);
     w[dst] = src[idx];
   }
-  // all puts of this CTA are visible system-wide before the CTA is counted
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(t.ctr, 1u);
-    if (prev == gridDim.x - 1) {
-      *t.ctr = 0;
-      __threadfence_system();
-      barrier_publish_wait(t, false);
-    }
-  }
+  dist_finish_put(t, gridDim.x);
 }
 
 // sum over ranks of `n` doubles, in rank order, result on every rank (one CTA)
@@ -170,6 +80,18 @@ static void fill_table(PeerTable *t) {
 }
 
 bool dist_active() { return ctx().nranks > 1 && g_dist.attached; }
+
+// Start an exchange epoch whose puts are issued by some other kernel (the fused FFT / Legendre stores): fills the
+// peer table (bases already point at W[epoch & 1]) and returns where this rank's new block will land.
+int dist_begin_put(PeerTable *t, void **landed) {
+  Context &c = ctx();
+  if (!g_dist.attached) return fail(MLEGS_E_COMM, "scalar_exchange: multi-rank exchange window is not attached");
+  fill_table(t);
+  t->epoch = ++g_dist.epoch;
+  t->data_off = win_data_offset() + (size_t)(t->epoch & 1) * g_dist.wstride;
+  *landed = reinterpret_cast<char *>(g_dist.base[c.rank]) + t->data_off;
+  return MLEGS_OK;
+}
 
 // Sum `n` device doubles over all ranks (no-op on one rank).
 int dist_allreduce(double *d_inout, int n) {

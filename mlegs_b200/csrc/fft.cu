@@ -12,7 +12,7 @@
 #include <cmath>
 #include <cstdio>
 
-#include "kernels.h"
+#include "dist_dev.cuh"
 
 namespace mlegs {
 
@@ -293,6 +293,19 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
       break;
   }
   prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
+                               const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
+                               cudaStream_t st) {
+  if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: the fused exchange needs the register kernels");
+  prof_begin("fft_phi_forward_put", st);
+  int rc = launch_fft_reg(FFT_R2C_FWD, plan.n, in, nullptr, rows * nz, rows, plane, rows, tw, tw_order, scale, nullptr, 0, 0,
+                          st, &peer, nrdim);
+  prof_end(st);
+  MLEGS_TRY(rc);
   KERNEL_CHECK();
   return MLEGS_OK;
 }

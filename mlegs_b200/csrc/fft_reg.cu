@@ -10,7 +10,7 @@
 // in memory (the radial index is the fastest one), so global accesses are coalesced 16-byte vectors and
 // every element is read once and written once.  All E loads of a thread are issued before the first
 // butterfly (memory-level parallelism = E x 16 B per thread).
-#include "kernels.h"
+#include "dist_dev.cuh"
 
 namespace mlegs {
 
@@ -164,6 +164,11 @@ struct FftRegArgs {
   double scale;
   const int *colstart;   // compact mode (axial FFT of the retained lines only): prefix sums of nn(m) per column
   int ncols, nrl;
+  // fused exchange(2,1) (FFT_R2C_FWD on several ranks): output column m goes straight into the window of the rank
+  // that owns m, at row r_off[me] + i of its (nrdim, m_cnt, nz) block; the kernel ends with the exchange barrier
+  int use_peer;
+  int nrdim;
+  PeerTable pt;
 };
 
 // MODE: FFT_C2C_FWD / FFT_C2C_BWD / FFT_R2C_FWD / FFT_C2R_BWD (kernels.h).
@@ -268,8 +273,22 @@ __global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
       cplx d = csub(zm, zc);
       cplx o = make_double2(0.5 * d.y, -0.5 * d.x);   // (-i/2) d
       cplx x = cadd(e, cmul(__ldg(&a.tw[m]), o));
-      if (ok) gout[(long long)m * a.stride_pt] = make_double2(x.x * a.scale, x.y * a.scale);
+      if (ok) {
+        const cplx val = make_double2(x.x * a.scale, x.y * a.scale);
+        if (a.use_peer) {
+          const long long kk = q / a.batch0;                 // z plane
+          const int ii = (int)(q - kk * a.batch0);           // local row
+          int dq;
+          size_t dst;
+          slab_put_index(0, a.pt.rank, a.pt.nranks, a.pt.r_cnt, a.pt.r_off, a.pt.m_cnt, a.pt.m_off, a.nrdim, 0, ii, m,
+                         (int)kk, &dq, &dst);
+          reinterpret_cast<cplx *>(reinterpret_cast<char *>(a.pt.base[dq]) + a.pt.data_off)[dst] = val;
+        } else {
+          gout[(long long)m * a.stride_pt] = val;
+        }
+      }
     }
+    if (a.use_peer) dist_finish_put(a.pt, gridDim.x);
     return;
   }
 
@@ -330,8 +349,11 @@ bool fft_reg_supported(int n) { return n == 32 || n == 64 || n == 128 || n == 25
 
 int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
                    long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
-                   const int *colstart, int ncols, int nrl, cudaStream_t st) {
+                   const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer, int nrdim) {
   FftRegArgs a;
+  a.use_peer = peer != nullptr;
+  a.nrdim = nrdim;
+  if (peer) a.pt = *peer;
   a.in = in;
   a.out = out;
   a.nlines = nlines;

@@ -24,9 +24,15 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
 
 // fft_reg.cu: register-resident fast path for power-of-two lengths 32..1024
 bool fft_reg_supported(int n);
+struct PeerTable;   // dist_dev.cuh
 int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
                    long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
-                   const int *colstart, int ncols, int nrl, cudaStream_t st);
+                   const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer = nullptr,
+                   int nrdim = 0);
+// azimuthal r2c FFT whose stores are the exchange(2,1) puts (several ranks, register kernels only)
+int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
+                               const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
+                               cudaStream_t st);
 // axial FFT of the retained lines only (rows < nn(m) of each local column); colstart = device prefix sums
 int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
                          int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,
@@ -49,6 +55,8 @@ struct LegArgs {
   double lnval;          // s%ln (log-term), applied on global m == 0
   int swap_parity;       // forward only: 0 = eomul (even rows <- even fold), 1 = oemul (ops:2067-2145)
   int skip_m0;           // forward only: leave the m == 0 column zero (vec2tp: `if (mv .ne. 0)`)
+  const PeerTable *peer; // backward only (host pointer, nullptr on one rank): the stores are the exchange(1,2) puts
+  int npdim;             // global number of m columns (fused put addressing)
 };
 int setup_leg_kernels();
 int launch_leg_forward(const LegArgs &a, cudaStream_t st);

@@ -17,7 +17,10 @@
 // stream into shared memory while the tensor pipe works on chunk c, and the parity fold (f(i) +- f(nr-1-i))
 // times the quadrature weight is applied when the B fragments are read.  8 warps: 2 parities x (2 x 2)
 // warp tiles of 32 x 32, 16 DMMA tiles per warp per k-step.
-#include "kernels.h"
+#include <algorithm>
+#include <cstring>
+
+#include "dist_dev.cuh"
 
 namespace mlegs {
 
@@ -214,10 +217,10 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
     issue_A(0, 0);
     issue_raw(0, 0);
     cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-    if (nchunks > 1) issue_raw(1, 1);
+    if (nchunks > 1) issue_raw(1, 1);       // both raw chunks travel together: one DRAM latency, not two
     cp_async_commit();
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    __syncthreads();
     fold(0, 0, 0);
     switch (nact) {
       case 4: mainloop(IntC<4>{}); break;
@@ -251,6 +254,14 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
     const int n = n0 + nl, kz = kz0 + kzl;
     if (n < a.nrdim && kz < a.nzl) out[(size_t)kz * col_stride + n] = cs[kzl][nl];
   }
+  // the grid only covers rows below the largest nn(m); the last row tile zeroes the rest (se = 0, ops:1898-1899)
+  if (blockIdx.y == gridDim.y - 1) {
+    const int nfirst = n0 + LEG_MT_F, nrest = a.nrdim - nfirst;
+    for (int p = tid; p < nrest * LEG_NTC; p += LEG_THREADS) {
+      const int n = nfirst + p % nrest, kz = kz0 + p / nrest;
+      if (kz < a.nzl) out[(size_t)kz * col_stride + n] = make_double2(0.0, 0.0);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,7 +273,10 @@ struct BwdSmem {
   double B[LEG_NTC][LEG_LDB_B];          // raw coefficients a(n, kz), n = 32 consecutive, (re, im) interleaved
 };
 
-__global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a) {
+// PUT: the physical-space rows are stored straight into the windows of the ranks that own them (exchange(1,2) fused
+// into the epilogue) and the kernel ends with the exchange barrier.
+template <bool PUT>
+__global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a, PeerTable pt) {
   extern __shared__ __align__(16) unsigned char smraw[];
   BwdSmem *sm = reinterpret_cast<BwdSmem *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -382,8 +396,19 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
         top.x += a.lnval * __ldg(&a.lnx[ii]);
         bot.x += a.lnval * __ldg(&a.lnx[a.nr - 1 - ii]);
       }
-      out[(size_t)kz * col_stride + ii] = top;
-      out[(size_t)kz * col_stride + (a.nr - 1 - ii)] = bot;
+      if (PUT) {
+        int dq;
+        size_t dst;
+        slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, ii, ml, kz, &dq,
+                       &dst);
+        reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = top;
+        slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, a.nr - 1 - ii, ml,
+                       kz, &dq, &dst);
+        reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = bot;
+      } else {
+        out[(size_t)kz * col_stride + ii] = top;
+        out[(size_t)kz * col_stride + (a.nr - 1 - ii)] = bot;
+      }
     }
   }
   // rows nr .. nrdim-1 are zero after rtrans_backward (se = 0 initialisation, ops:1975-1976)
@@ -391,22 +416,38 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a)
     int npad = a.nrdim - a.nr;
     for (int idx = tid; idx < npad * LEG_NTC; idx += LEG_THREADS) {
       int r = idx % npad, kz = kz0 + idx / npad;
-      if (kz < a.nzl) out[(size_t)kz * col_stride + a.nr + r] = make_double2(0.0, 0.0);
+      if (kz < a.nzl) {
+        if (PUT) {
+          int dq;
+          size_t dst;
+          slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, a.nr + r, ml, kz,
+                         &dq, &dst);
+          reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = make_double2(0.0, 0.0);
+        } else {
+          out[(size_t)kz * col_stride + a.nr + r] = make_double2(0.0, 0.0);
+        }
+      }
     }
   }
+  if (PUT) dist_finish_put(pt, gridDim.x * gridDim.y * gridDim.z);
 }
 
 int setup_leg_kernels() {
   CUDA_TRY(cudaFuncSetAttribute(leg_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(FwdSmem)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(2 * sizeof(BwdSmem))));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(2 * sizeof(BwdSmem))));
   return MLEGS_OK;
 }
 
 int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
-  dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrdim + LEG_MT_F - 1) / LEG_MT_F, a.npl);
+  // row tiles: up to the largest truncation among the local columns (the last tile zero-fills rows beyond it)
+  int nn_max = (a.m0 < a.npc) ? std::max(std::min(a.nrc, a.nrc - a.m0), 0) : 0;
+  nn_max = std::max(1, std::min(nn_max, a.nrdim));
+  dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (nn_max + LEG_MT_F - 1) / LEG_MT_F, a.npl);
   prof_begin("legendre_forward", st);
   leg_forward_kernel<<<grid, LEG_THREADS, sizeof(FwdSmem), st>>>(a);
   prof_end(st);
@@ -417,8 +458,14 @@ int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
 int launch_leg_backward(const LegArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrh + LEG_MT_B - 1) / LEG_MT_B, a.npl);
-  prof_begin("legendre_backward", st);
-  leg_backward_kernel<<<grid, LEG_THREADS, 2 * sizeof(BwdSmem), st>>>(a);
+  prof_begin(a.peer ? "legendre_backward_put" : "legendre_backward", st);
+  if (a.peer) {
+    leg_backward_kernel<true><<<grid, LEG_THREADS, 2 * sizeof(BwdSmem), st>>>(a, *a.peer);
+  } else {
+    PeerTable none;
+    memset(&none, 0, sizeof(none));
+    leg_backward_kernel<false><<<grid, LEG_THREADS, 2 * sizeof(BwdSmem), st>>>(a, none);
+  }
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;

@@ -15,7 +15,8 @@ int trans_impl(mlegs_field *s, const char *to);
 int dist_allreduce(double *d_inout, int n);   // dist.cu: sum over ranks, identical result everywhere
 int dist_check_timeout();
 int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst);
-int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst);
+struct PeerTable;
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer = nullptr);
 
 static cudaStream_t strm() { return (cudaStream_t)ctx().stream; }
 static size_t nelem(const mlegs_field *f) { return (size_t)f->loc_sz[0] * f->loc_sz[1] * f->loc_sz[2]; }
@@ -753,6 +754,8 @@ int vec2tp_impl(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field 
   g.npc = ci.npc;
   g.nrdim = c.nrdim;
   g.lnval = 0.0;
+  g.peer = nullptr;
+  g.npdim = c.npdim;
   cplx *T = (cplx *)c.d_scratch[2];
   g.out = T;
   TpCombineArgs t;

@@ -7,11 +7,12 @@
 #include <cstring>
 #include <vector>
 
-#include "kernels.h"
+#include "dist_dev.cuh"
 
 namespace mlegs {
 
 int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, void **landed);   // dist.cu
+int dist_begin_put(PeerTable *t, void **landed);                                                  // dist.cu
 
 static int space_id(const char *sp) {
   if (!strncmp(sp, "PPP", 3)) return 0;
@@ -53,6 +54,8 @@ static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
   a->lnval = s->ln;
   a->swap_parity = 0;
   a->skip_m0 = 0;
+  a->peer = nullptr;
+  a->npdim = c.npdim;
   return MLEGS_OK;
 }
 
@@ -104,11 +107,13 @@ static int stage_z_compact(const mlegs_field *s, bool forward, const cplx *src, 
                               c.cs_total, plane, c.d_tw_z, c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st);
 }
 
-int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer = nullptr);
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer) {
   LegArgs a;
   MLEGS_TRY(rtrans_args(s, forward ? "rtrans_forward" : "rtrans_backward", &a));
   a.in = src;
   a.out = dst;
+  a.peer = peer;
   cudaStream_t st = (cudaStream_t)ctx().stream;
   return forward ? launch_leg_forward(a, st) : launch_leg_backward(a, st);
 }
@@ -126,7 +131,7 @@ int trans_impl(mlegs_field *s, const char *to) {
   const bool multi = c.nranks > 1 && has_p;
 
   const bool compact_ok = has_z && fft_reg_supported(c.plan_z.n);
-  bool rows_zero = false;
+  bool rows_zero = false, exchanged = false;
   cplx *home = (cplx *)s->e;
   cplx *tmp = (cplx *)c.d_scratch[0];
   cplx *at = home;   // where the data currently lives
@@ -136,11 +141,22 @@ int trans_impl(mlegs_field *s, const char *to) {
     while (cur < dst) {
       if (cur == 0) {
         if (has_p) {
-          if (multi) {
-            // FFT in place, then the (2,1) exchange moves the block into the other buffer
+          if (multi && fft_reg_supported(c.plan_p.n)) {
+            // the FFT's stores ARE the (2,1) exchange: every output column goes straight into the window of the
+            // rank that owns that m, and the kernel ends with the exchange barrier
+            PeerTable pt;
+            void *landed = nullptr;
+            MLEGS_TRY(dist_begin_put(&pt, &landed));
+            const long long rows = s->loc_sz[0];
+            MLEGS_TRY(launch_fft_phi_forward_put(c.plan_p, at, rows, s->loc_sz[2], rows * (long long)s->loc_sz[1],
+                                                 c.d_tw_p, c.p.np, 1.0 / c.p.np, pt, c.nrdim, st));
+            field_set_layout(s, false);
+            at = (cplx *)landed;
+          } else if (multi) {
+            // FFT in place, then the (2,1) exchange moves the block into this rank's receive window
             MLEGS_TRY(stage_phi(s, true, at, at));
             void *landed = nullptr;
-            MLEGS_TRY(exchange_slab(s, 2, 1, at, &landed));   // lands in this rank's receive window
+            MLEGS_TRY(exchange_slab(s, 2, 1, at, &landed));
             at = (cplx *)landed;
           } else {
             // go out of place when the Legendre stage follows, so that it lands back at home and the axial
@@ -180,14 +196,27 @@ int trans_impl(mlegs_field *s, const char *to) {
           at = o;
         }
       } else if (cur == 2) {
-        MLEGS_TRY(stage_r(s, false, at, other(at)));  // + ln term (ops:219-221) fused into the epilogue
-        at = other(at);
+        if (multi && dst == 0) {
+          // the epilogue's stores ARE the (1,2) exchange (rows go to the ranks that own them in physical space)
+          PeerTable pt;
+          void *landed = nullptr;
+          MLEGS_TRY(dist_begin_put(&pt, &landed));
+          MLEGS_TRY(stage_r(s, false, at, nullptr, &pt));
+          field_set_layout(s, true);
+          at = (cplx *)landed;
+          exchanged = true;
+        } else {
+          MLEGS_TRY(stage_r(s, false, at, other(at)));  // + ln term (ops:219-221) fused into the epilogue
+          at = other(at);
+        }
       } else if (cur == 1) {
         if (has_p) {
           if (multi) {
-            void *landed = nullptr;
-            MLEGS_TRY(exchange_slab(s, 1, 2, at, &landed));
-            at = (cplx *)landed;
+            if (!exchanged) {
+              void *landed = nullptr;
+              MLEGS_TRY(exchange_slab(s, 1, 2, at, &landed));
+              at = (cplx *)landed;
+            }
             cplx *o = home;
             MLEGS_TRY(stage_phi(s, false, at, o));
             at = o;
@@ -239,6 +268,64 @@ int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], do
   MLEGS_TRY(trans_impl(&f, to));
   n = (size_t)f.loc_sz[0] * f.loc_sz[1] * f.loc_sz[2];
   CUDA_TRY(cudaMemcpyAsync(host_e, f.e, n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MLEGS_OK;
+}
+
+// Batched host entry: the n host arrays are independent scalars (e.g. the three components a tp2vec caller
+// transforms back to back).  Three staging scalars and two copy streams keep PCIe busy in both directions:
+// the H2D copy of field j+1 and the D2H copy of field j-1 overlap the transform of field j.
+int mlegs_b200_trans_host_batch(int n, void *const *host_e, const char from[3], const char to[3], const double *ln) {
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  if (space_id(from) < 0)
+    return fail(MLEGS_E_ARG, "trans: scalar space info corrupted (only accepting PPP, PFP, FFP and FFF)");
+  if (space_id(to) < 0) return fail(MLEGS_E_ARG, "trans: only taking PPP, PFP, FFP and FFF for spectral transformation");
+  cudaStream_t st = (cudaStream_t)c.stream;
+  const int NB = 3;
+  static mlegs_field f[NB];
+  static size_t f_bytes = 0;
+  static cudaStream_t s_in = nullptr, s_out = nullptr;
+  static cudaEvent_t in_done[NB], comp_done[NB], out_done[NB];
+  if (!s_in) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < NB; ++b) {
+      CUDA_TRY(cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
+    }
+  }
+  if (f_bytes != c.field_bytes) {
+    for (int b = 0; b < NB; ++b) {
+      if (f[b].e) cudaFree(f[b].e);
+      f[b].e = nullptr;
+      CUDA_TRY(cudaMalloc(&f[b].e, c.field_bytes));
+    }
+    f_bytes = c.field_bytes;
+  }
+  // the copy streams start after everything already queued on the compute stream
+  CUDA_TRY(cudaEventRecord(comp_done[0], st));
+  CUDA_TRY(cudaStreamWaitEvent(s_in, comp_done[0], 0));
+  for (int j = 0; j < n; ++j) {
+    const int b = j % NB;
+    if (j >= NB) CUDA_TRY(cudaStreamWaitEvent(s_in, out_done[b], 0));   // staging buffer b is free again
+    field_set_layout(&f[b], space_id(from) == 0);
+    f[b].nrchop_offset = f[b].npchop_offset = f[b].nzchop_offset = 0;
+    set_space(&f[b], space_id(from));
+    f[b].ln = ln ? ln[j] : 0.0;
+    size_t ne = (size_t)f[b].loc_sz[0] * f[b].loc_sz[1] * f[b].loc_sz[2];
+    CUDA_TRY(cudaMemcpyAsync(f[b].e, host_e[j], ne * sizeof(cplx), cudaMemcpyHostToDevice, s_in));
+    CUDA_TRY(cudaEventRecord(in_done[b], s_in));
+    CUDA_TRY(cudaStreamWaitEvent(st, in_done[b], 0));
+    MLEGS_TRY(trans_impl(&f[b], to));
+    CUDA_TRY(cudaEventRecord(comp_done[b], st));
+    CUDA_TRY(cudaStreamWaitEvent(s_out, comp_done[b], 0));
+    ne = (size_t)f[b].loc_sz[0] * f[b].loc_sz[1] * f[b].loc_sz[2];
+    CUDA_TRY(cudaMemcpyAsync(host_e[j], f[b].e, ne * sizeof(cplx), cudaMemcpyDeviceToHost, s_out));
+    CUDA_TRY(cudaEventRecord(out_done[b], s_out));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s_out));
   CUDA_TRY(cudaStreamSynchronize(st));
   return MLEGS_OK;
 }

@@ -112,6 +112,18 @@ def trans_host(host_e: np.ndarray, from_space: str, to_space: str, ln: float = 0
     check(_l().mlegs_b200_trans_host(host_e.ctypes.data_as(C.c_void_p), from_space.encode(), to_space.encode(), ln))
 
 
+def trans_host_batch(host_arrays, from_space: str, to_space: str, ln=None):
+    """trans_host for several independent host arrays, pipelined over PCIe (H2D / transform / D2H overlap)."""
+    n = len(host_arrays)
+    for a in host_arrays:
+        assert a.flags.f_contiguous and a.dtype == np.complex128
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in host_arrays])
+    lnv = None
+    if ln is not None:
+        lnv = (C.c_double * n)(*[float(v) for v in ln])
+    check(_l().mlegs_b200_trans_host_batch(n, ptrs, from_space.encode(), to_space.encode(), lnv))
+
+
 def chop(s): check(_l().mlegs_b200_chop(C.byref(s.f)))
 def dealias(s): check(_l().mlegs_b200_dealias(C.byref(s.f)))
 

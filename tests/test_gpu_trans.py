@@ -133,3 +133,14 @@ def test_roundtrip_128_config_and_host_entry():
     mb.trans_host(h, "PPP", "FFF")
     assert rel_l2(h, so.e) < TOL
     assert mb.launch_count() > 0
+    # the pipelined batch entry gives the same numbers, field by field
+    hs = [random_fff(ok, seed=sd).copy(order="F") for sd in (0, 3, 4, 5, 6)]
+    want = []
+    for h0 in hs:
+        t = mo.Scalar(e=h0.copy(order="F"), space="FFF")
+        mo.trans(t, "PPP", ok)
+        want.append(t.e)
+    mb.trans_host_batch(hs, "FFF", "PPP")
+    for got, w in zip(hs, want):
+        assert rel_l2(got, w) < TOL
+    assert rel_l2(hs[0], ppp) < TOL
