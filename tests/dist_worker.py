@@ -107,11 +107,11 @@ def run_case(nr, np_, nz, nrc, npc, nzc, ell, hp, rank, world, steps):
     mb.idel2(s)
     mo.idel2_proln(so, ok)
     check("idel2", s, so.e, tol=1e-10)
-    assert abs(s.ln - so.ln) <= 1e-10 * max(1.0, abs(so.ln)), (s.ln, so.ln)   # ln is broadcast to every rank
+    assert abs(s.ln - so.ln) <= 1e-8 * max(1.0, abs(so.ln)), (s.ln, so.ln)   # ln is broadcast to every rank
     mb.idelsqp(s)
     mo.idelsqp(so, ok)
     check("idelsqp", s, so.e, tol=1e-10)
-    assert abs(s.ln - so.ln) <= 1e-10 * max(1.0, abs(so.ln)), (s.ln, so.ln)
+    assert abs(s.ln - so.ln) <= 1e-8 * max(1.0, abs(so.ln)), (s.ln, so.ln)
     if hp:
         mb.ihelmp(s, hp, -3.0e6, 0.5)
         mo.ihelmp(so, hp, -3.0e6, 0.5, ok)
