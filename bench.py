@@ -33,9 +33,13 @@ METRIC = "transform_roundtrip_gdofs"
 UNIT = "GDOF/s"
 
 
-def workload(size: int):
-    return dict(nr=size, np=size, nz=size, nrchop=size, npchop=size // 2 + 1, nzchop=size // 2 + 1,
-                ell=4.0, zlen=2.0 * np.pi)
+def workload(size: int, world: int = 1, weak: str = "nz"):
+    """N = 1: the cubic case.  N > 1, weak scaling: the periodic axial direction is extended with the GPU count
+    (NZ = size * N, ZLEN scaled alike), so every GPU keeps size^3 degrees of freedom of every field and the same
+    Legendre/FFT work per field as the single-GPU run; --weak fields keeps the cube and grows the batch instead."""
+    nz = size * world if weak == "nz" else size
+    return dict(nr=size, np=size, nz=nz, nrchop=size, npchop=size // 2 + 1, nzchop=nz // 2 + 1,
+                ell=4.0, zlen=2.0 * np.pi * (nz // size))
 
 
 def measured_peaks():
@@ -141,7 +145,7 @@ def run_reference(args):
         return
     import mlegs_b200 as mb
     from helpers import oracle_params
-    wl = workload(args.size)
+    wl = workload(args.size, args.gpus, args.weak)
     p = mb.make_params(wl["nr"], wl["np"], wl["nz"], wl["nrchop"], wl["npchop"], wl["nzchop"], ell=wl["ell"],
                        zlen=wl["zlen"])
     kit = mb.TfmKit.build_tables(p)          # host-only table build (no GPU work)
@@ -160,7 +164,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([t for _, t in per_step]) * 1e3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"PPP<->FFF round trip {args.size}^3 (BASELINE.json configs[1])",
+            "config": {"workload": f"PPP<->FFF round trip {wl['nr']}x{wl['np']}x{wl['nz']}",
                        "fields_per_step": nfields, **{k: (float(v) if isinstance(v, float) else v) for k, v in wl.items()}},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port",
                              "sample": f"{nfields} fields x 1 round trip per step, NumPy oracle port "
@@ -190,7 +194,7 @@ def run_native(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    wl = workload(args.size)
+    wl = workload(args.size, world, args.weak)
     p = mb.make_params(wl["nr"], wl["np"], wl["nz"], wl["nrchop"], wl["npchop"], wl["nzchop"], ell=wl["ell"],
                        zlen=wl["zlen"])
     # N > 1: every field is slab-distributed over all ranks like the reference's MPI run (PPP sharded in r,
@@ -201,8 +205,10 @@ def run_native(args):
     dof = wl["nr"] * wl["np"] * wl["nz"]
     field_bytes = int(np.prod(kit.glb_sz)) * 16
     # fields per GPU-equivalent: the batch is > 2x L2 and long enough for the clock sampler to see it
-    nf = args.fields or max(2, int(np.ceil(2.2 * 126e6 / field_bytes)), min(64, int(1.2e9 // field_bytes)))
-    nfields = nf * world          # weak scaling: per-GPU work (nf field-equivalents) is fixed
+    gpu_bytes = field_bytes // world      # one field's share on one GPU
+    nf = args.fields or max(2, int(np.ceil(2.2 * 126e6 / gpu_bytes)), min(64, int(1.2e9 // gpu_bytes)))
+    # weak scaling, per-GPU work fixed: either the fields grow with N (default) or the batch does
+    nfields = nf if args.weak == "nz" else nf * world
     stream = torch.cuda.Stream()
     mb.set_stream(stream.cuda_stream)
 
@@ -360,10 +366,14 @@ def run_native(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"PPP<->FFF round trip {args.size}^3 (BASELINE.json configs[1])",
-                           "fields_per_step": nfields, "fields_per_step_per_gpu": nf,
+                "config": {"workload": (f"PPP<->FFF round trip {wl['nr']}x{wl['np']}x{wl['nz']} "
+                                        + ("(BASELINE.json configs[1])" if world == 1 else
+                                           f"(configs[1] extended along the periodic axis: {args.size}^3 DOF per GPU, "
+                                           "BASELINE.json configs[4] sweep shape)" if args.weak == "nz" else
+                                           "(BASELINE.json configs[1], batch grown with N)")),
+                           "fields_per_step": nfields,
                            "l2_policy": f"inputs larger than L2: {nfields} distinct fields x {field_bytes / 1e6:.1f} MB "
-                                        f"({nf * field_bytes / 1e6:.0f} MB per GPU)",
+                                        f"({nfields * gpu_bytes / 1e6:.0f} MB per GPU)",
                            "parallelism": par,
                            **{k: (float(v) if isinstance(v, float) else v) for k, v in wl.items()}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
@@ -384,6 +394,8 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--fields", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--weak", default="nz", choices=["nz", "fields"],
+                    help="N > 1: grow NZ with N (default, DOF per GPU fixed) or grow the batch of cubic fields")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -123,88 +123,150 @@ __device__ __forceinline__ int k_visits(int k, int nzl, int nzc, int nzcu) {
   return v;
 }
 
-__global__ void band_op_kernel(BandOpArgs a) {
+// One CTA per (column m, block of KB axial planes).  A thread owns one radial row i for all KB planes, so its band
+// coefficients are loaded once and reused KB times; planes are staged in shared memory ([plane][row], row fastest:
+// conflict-free, coalesced), which also makes the in-place update safe.  The -k^2 shift of the diagonal is applied
+// per plane.  `reps` keeps the reference's habit of visiting the plane k = nz/2 twice when nzchop = nz/2 + 1.
+#define BAND_KB_MAX 8
+template <int NB>
+__global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  cplx *s0 = reinterpret_cast<cplx *>(smraw);
-  cplx *b1 = s0 + a.nrl, *b2 = b1 + a.nrl, *s2 = b2 + a.nrl;
-  const int j = blockIdx.x, k = blockIdx.y;
+  cplx *bufs = reinterpret_cast<cplx *>(smraw);
+  const size_t bsz = (size_t)KB * a.nrl;
+  cplx *cur = bufs, *nxt = bufs + bsz, *s0 = bufs + 2 * bsz, *s2 = bufs + 3 * bsz;   // s0/s2 only with combine
+  const int j = blockIdx.x, k0 = blockIdx.y * KB;
   const int mglob = a.m0 + j;
   const int nn = nn_of(mglob, a.nrc, a.npc);
-  const int reps = (nn >= 1) ? k_visits(k, a.nzl, a.nzc, a.nzcu) : 0;
-  const bool lncol = (mglob == 0 && k == 0 && a.nlnc > 0);
-  if (!a.combine && reps == 0 && !lncol) return;
-  cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
-  const double *tab = a.tab + (size_t)mglob * a.nb * a.ne;
-  const int half = a.nb / 2;
-  double ak2 = 0.0;
-  if (a.ak) {
-    double akv = a.ak[k];
-    ak2 = akv * akv;
-  }
-  for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
-    cplx v = col[i];
-    s0[i] = v;
-    b1[i] = v;
+  constexpr int half = NB / 2;
+  const double *tab = a.tab + (size_t)mglob * NB * a.ne;
+  __shared__ int s_reps[BAND_KB_MAX];
+  __shared__ double s_ak2[BAND_KB_MAX];
+  __shared__ int s_any, s_max;
+  if (threadIdx.x < KB) {
+    const int k = k0 + threadIdx.x;
+    int reps = (k < a.nzl && nn >= 1) ? k_visits(k, a.nzl, a.nzc, a.nzcu) : 0;
+    s_reps[threadIdx.x] = reps;
+    double akv = (a.ak && k < a.nzl) ? a.ak[k] : 0.0;
+    s_ak2[threadIdx.x] = akv * akv;
   }
   __syncthreads();
-  cplx *cur = b1, *nxt = b2;
+  if (threadIdx.x == 0) {
+    int mx = 0;
+    for (int kk = 0; kk < KB; ++kk) mx = max(mx, s_reps[kk]);
+    s_max = mx;
+    s_any = (mx > 0) || a.combine || (mglob == 0 && k0 == 0 && a.nlnc > 0);
+  }
+  __syncthreads();
+  if (!s_any) return;
+  const int maxreps = s_max;
+  const bool lnblk = (mglob == 0 && k0 == 0 && a.nlnc > 0);
+
+  // ---- stage the planes ----
+  for (int kk = 0; kk < KB; ++kk) {
+    const int k = k0 + kk;
+    if (k >= a.nzl) break;
+    const cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+    for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
+      cplx v = col[i];
+      cur[kk * a.nrl + i] = v;
+      if (a.combine) s0[kk * a.nrl + i] = v;
+    }
+  }
+  __syncthreads();
+
+  const bool direct = (a.napply == 1 && !a.combine && maxreps <= 1 && !lnblk);
   for (int ap = 0; ap < a.napply; ++ap) {
-    for (int r = 0; r < reps; ++r) {
+    for (int r = 0; r < maxreps; ++r) {
       for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
-        cplx o = cur[i];
-        if (i < nn) {
-          double ar = 0.0, ai = 0.0;
-          for (int b = 0; b < a.nb; ++b) {
-            int jj = i + b - half;
-            if (jj < 0 || jj >= nn) continue;
-            double cf = tab[(size_t)b * a.ne + i];
-            if (b == half && a.ak) cf = cf - ak2;
-            cplx x = cur[jj];
-            ar = ar + x.x * cf;
-            ai = ai + x.y * cf;
-          }
-          o = make_double2(ar, ai);
+        double cf[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int jj = i + b - half;
+          cf[b] = (i < nn && jj >= 0 && jj < nn) ? __ldg(&tab[(size_t)b * a.ne + i]) : 0.0;
         }
-        nxt[i] = o;
+        for (int kk = 0; kk < KB; ++kk) {
+          const int k = k0 + kk;
+          if (k >= a.nzl) break;
+          const cplx *c0 = cur + kk * a.nrl;
+          cplx o = c0[i];
+          if (i < nn && r < s_reps[kk]) {
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const int jj = i + b - half;
+              if (jj < 0 || jj >= nn) continue;
+              double c = cf[b];
+              if (b == half && a.ak) c = c - s_ak2[kk];
+              cplx x = c0[jj];
+              ar = ar + x.x * c;
+              ai = ai + x.y * c;
+            }
+            o = make_double2(ar, ai);
+            if (direct) a.e[((size_t)k * a.npl + j) * a.nrl + i] = o;
+          }
+          if (!direct) nxt[kk * a.nrl + i] = o;
+        }
       }
+      if (direct) return;
       __syncthreads();
       cplx *t = cur;
       cur = nxt;
       nxt = t;
     }
     if (ap == 0) {
-      if (lncol) {
-        if (threadIdx.x < a.nlnc) cur[threadIdx.x].x = cur[threadIdx.x].x + a.lnc[threadIdx.x];
+      if (lnblk) {
+        if (threadIdx.x < a.nlnc) {   // plane k = 0
+          const double add = threadIdx.x == 0 ? a.lnc[0] : (threadIdx.x == 1 ? a.lnc[1] : a.lnc[2]);
+          cur[threadIdx.x].x = cur[threadIdx.x].x + add;
+        }
         __syncthreads();
       }
       if (a.combine) {
-        for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) s2[i] = cur[i];
+        for (int kk = 0; kk < KB; ++kk)
+          for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) s2[kk * a.nrl + i] = cur[kk * a.nrl + i];
         __syncthreads();
       }
     }
   }
-  for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
-    cplx o = cur[i];
-    if (a.combine) {
-      cplx q = s2[i], s = s0[i];
-      o = make_double2((o.x + a.beta * q.x) + a.alpha * s.x, (o.y + a.beta * q.y) + a.alpha * s.y);
+  for (int kk = 0; kk < KB; ++kk) {
+    const int k = k0 + kk;
+    if (k >= a.nzl) break;
+    if (!a.combine && s_reps[kk] == 0 && !(lnblk && kk == 0)) continue;   // untouched plane
+    cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+    for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
+      cplx o = cur[kk * a.nrl + i];
+      if (a.combine) {
+        cplx q = s2[kk * a.nrl + i], s = s0[kk * a.nrl + i];
+        o = make_double2((o.x + a.beta * q.x) + a.alpha * s.x, (o.y + a.beta * q.y) + a.alpha * s.y);
+      }
+      col[i] = o;
     }
-    col[i] = o;
   }
 }
 
 int launch_band_op(const BandOpArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
-  size_t smem = (size_t)4 * a.nrl * sizeof(cplx);
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(band_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
+  const int nbuf = a.combine ? 4 : 2;
+  int KB = BAND_KB_MAX;
+  while (KB > 1 && (size_t)nbuf * KB * a.nrl * sizeof(cplx) > 72 * 1024) KB >>= 1;
+  size_t smem = (size_t)nbuf * KB * a.nrl * sizeof(cplx);
+  if (smem > 220 * 1024) return fail(MLEGS_E_ARG, "band operator: radial size too large for shared memory");
+  static size_t attr_set3 = 0, attr_set5 = 0;
+  if (a.nb == 3 && smem > 48 * 1024 && smem > attr_set3) {
+    CUDA_TRY(cudaFuncSetAttribute(band_op_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set3 = smem;
   }
-  dim3 grid(a.npl, a.nzl);
-  int threads = a.nrl >= 256 ? 256 : 128;
+  if (a.nb == 5 && smem > 48 * 1024 && smem > attr_set5) {
+    CUDA_TRY(cudaFuncSetAttribute(band_op_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set5 = smem;
+  }
+  dim3 grid(a.npl, (a.nzl + KB - 1) / KB);
+  int threads = std::min(1024, (a.nrl + 31) / 32 * 32);
   prof_begin(a.combine ? "helmp_band" : (a.nb == 3 ? "xxdx_band" : "del2_band"), st);
-  band_op_kernel<<<grid, threads, smem, st>>>(a);
+  if (a.nb == 3)
+    band_op_kernel<3><<<grid, threads, smem, st>>>(a, KB);
+  else
+    band_op_kernel<5><<<grid, threads, smem, st>>>(a, KB);
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
@@ -499,65 +561,96 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
     }
     __syncwarp();
     // ---- forward sweep (zgbtrs, external/lapack/SRC/zgbtrs.f:205-232) ----
-    // multipliers of 4 columns per load: lane = 8 u + i holds L(i+1) of column jj0+u (kl <= 8)
-    for (int jj0 = 0; jj0 < nn; jj0 += 4) {
-      const int u_ld = lane >> 3, i_ld = lane & 7;
-      double lreg = 0.0;
-      if (jj0 + u_ld < nn && i_ld < kl) lreg = __ldg(&AB[(size_t)(jj0 + u_ld) * ldab + kv + 1 + i_ld]);
-      int preg = (lane < 4 && jj0 + lane < nn) ? (int)__ldg(&piv[jj0 + lane]) : 0;
+    // The factors do not depend on the right-hand side, so they are fetched 8 columns ahead of the dependent
+    // chain: lane = 8 u + i holds the multiplier L(i+1) of column jb + 4 h + u (kl <= 8), lanes 0..7 the pivots.
+    {
+      double lcur[2], lnxt[2] = {0.0, 0.0};
+      int pcur, pnxt = 0;
+      auto loadL = [&](int jb, double(&l)[2], int &pv) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int jj = jj0 + u;
-        if (jj >= nn) break;
-        const int km = min(kl, nn - 1 - jj);
-        const int jp = __shfl_sync(0xffffffffu, preg, u);
-        const double l = __shfl_sync(0xffffffffu, lreg, 8 * u + ((lane - 1) & 7));   // lane i (1..km) gets L(i)
-        if (jp != 0) {
-          if (lane == 0) {
-            double tr = rhs[2 * (jj + jp)], ti = rhs[2 * (jj + jp) + 1];
-            rhs[2 * (jj + jp)] = rhs[2 * jj];
-            rhs[2 * (jj + jp) + 1] = rhs[2 * jj + 1];
-            rhs[2 * jj] = tr;
-            rhs[2 * jj + 1] = ti;
-          }
-          __syncwarp();
+        for (int h = 0; h < 2; ++h) {
+          const int cc = jb + 4 * h + (lane >> 3);
+          l[h] = (cc < nn && (lane & 7) < kl) ? __ldg(&AB[(size_t)cc * ldab + kv + 1 + (lane & 7)]) : 0.0;
         }
-        if (km > 0) {
-          if (lane >= 1 && lane <= km) {
-            double tr = -rhs[2 * jj], ti = -rhs[2 * jj + 1];
-            rhs[2 * (jj + lane)] = rhs[2 * (jj + lane)] + l * tr;
-            rhs[2 * (jj + lane) + 1] = rhs[2 * (jj + lane) + 1] + l * ti;
+        pv = (lane < 8 && jb + lane < nn) ? (int)__ldg(&piv[jb + lane]) : 0;
+      };
+      loadL(0, lcur, pcur);
+      for (int jb = 0; jb < nn; jb += 8) {
+        if (jb + 8 < nn) loadL(jb + 8, lnxt, pnxt);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int jj = jb + u;
+          if (jj >= nn) break;
+          const int km = min(kl, nn - 1 - jj);
+          const int jp = __shfl_sync(0xffffffffu, pcur, u);
+          const double l = __shfl_sync(0xffffffffu, lcur[u >> 2], 8 * (u & 3) + ((lane - 1) & 7));   // lane i gets L(i)
+          if (jp != 0) {
+            if (lane == 0) {
+              double tr = rhs[2 * (jj + jp)], ti = rhs[2 * (jj + jp) + 1];
+              rhs[2 * (jj + jp)] = rhs[2 * jj];
+              rhs[2 * (jj + jp) + 1] = rhs[2 * jj + 1];
+              rhs[2 * jj] = tr;
+              rhs[2 * jj + 1] = ti;
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          if (km > 0) {
+            if (lane >= 1 && lane <= km) {
+              double tr = -rhs[2 * jj], ti = -rhs[2 * jj + 1];
+              rhs[2 * (jj + lane)] = rhs[2 * (jj + lane)] + l * tr;
+              rhs[2 * (jj + lane) + 1] = rhs[2 * (jj + lane) + 1] + l * ti;
+            }
+            __syncwarp();
+          }
         }
+        lcur[0] = lnxt[0];
+        lcur[1] = lnxt[1];
+        pcur = pnxt;
       }
     }
     // ---- ztbsv: upper, no transpose, non-unit, bandwidth kv ----
-    // U column of step jj: lane t holds U(jj - t, jj) = AB[kv - t], prefetched one step ahead
-    double unext = (lane <= kv && nn - 1 - lane >= 0) ? __ldg(&AB[(size_t)(nn - 1) * ldab + kv - lane]) : 0.0;
-    for (int jj = nn - 1; jj >= 0; --jj) {
-      const double u = unext;
-      if (jj > 0 && lane <= kv && lane <= jj - 1) unext = __ldg(&AB[(size_t)(jj - 1) * ldab + kv - lane]);
-      double xr = rhs[2 * jj], xi = rhs[2 * jj + 1];
-      if (xr != 0.0 || xi != 0.0) {
-        const double ujj = __shfl_sync(0xffffffffu, u, 0);
-        xr = xr / ujj;
-        xi = xi / ujj;
-        __syncwarp();
-        if (lane == 0) {
-          rhs[2 * jj] = xr;
-          rhs[2 * jj + 1] = xi;
+    // lane t holds U(jj - t, jj) = AB[jj*ldab + kv - t] of 8 consecutive steps, fetched 8 steps ahead
+    {
+      double ucur[8], unxt[8];
+      auto loadU = [&](int jtop, double(&u)[8]) {
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          const int cc = jtop - sidx;
+          u[sidx] = (cc >= 0 && lane <= kv && lane <= cc) ? __ldg(&AB[(size_t)cc * ldab + kv - lane]) : 0.0;
         }
-        const int cnt = min(jj, kv);
-        if (lane >= 1 && lane <= cnt) {
-          int i = jj - lane;
-          rhs[2 * i] = rhs[2 * i] - xr * u;
-          rhs[2 * i + 1] = rhs[2 * i + 1] - xi * u;
+      };
+      loadU(nn - 1, ucur);
+      for (int jt = nn - 1; jt >= 0; jt -= 8) {
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) unxt[sidx] = 0.0;
+        if (jt - 8 >= 0) loadU(jt - 8, unxt);
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          const int jj = jt - sidx;
+          if (jj < 0) break;
+          const double u = ucur[sidx];
+          double xr = rhs[2 * jj], xi = rhs[2 * jj + 1];
+          if (xr != 0.0 || xi != 0.0) {
+            const double ujj = __shfl_sync(0xffffffffu, u, 0);
+            xr = xr / ujj;
+            xi = xi / ujj;
+            __syncwarp();
+            if (lane == 0) {
+              rhs[2 * jj] = xr;
+              rhs[2 * jj + 1] = xi;
+            }
+            const int cnt = min(jj, kv);
+            if (lane >= 1 && lane <= cnt) {
+              int i = jj - lane;
+              rhs[2 * i] = rhs[2 * i] - xr * u;
+              rhs[2 * i + 1] = rhs[2 * i + 1] - xi * u;
+            }
+          }
+          __syncwarp();
         }
-      } else {
-        __shfl_sync(0xffffffffu, u, 0);
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) ucur[sidx] = unxt[sidx];
       }
-      __syncwarp();
     }
     for (int i = lane; i < nn; i += 32) col[i] = make_double2(rhs[2 * i], rhs[2 * i + 1]);
     __syncwarp();

@@ -53,7 +53,7 @@ __global__ void allreduce_small_kernel(PeerTable t, double *inout, int n, size_t
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) barrier_publish_wait(t, true);
+  if (threadIdx.x < 32) barrier_publish_wait(t, true);
   __syncthreads();
   const double *mine = reinterpret_cast<const double *>(reinterpret_cast<char *>(t.base[t.rank]) + red_off);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -67,14 +67,14 @@ struct PeerTable {
   int *flag;            // device error flags ([2] = exchange timeout)
 };
 
-// publish `epoch` to all peers and wait for theirs; called by one thread of the last CTA
+// publish `epoch` to all peers and wait for theirs; called by the first warp of the last CTA (one lane per peer, so
+// the remote stores and the polls of all peers are in flight together instead of one NVLink round trip each)
 __device__ __forceinline__ void barrier_publish_wait(const PeerTable &t, bool reduction) {
-  for (int q = 0; q < t.nranks; ++q) {
+  const int q = threadIdx.x;
+  if (q < t.nranks) {
     WinHeader *h = reinterpret_cast<WinHeader *>(t.base[q]);
     st_release_sys(reduction ? &h->red_arrive[t.rank] : &h->arrive[t.rank], t.epoch);
-  }
-  WinHeader *me = reinterpret_cast<WinHeader *>(t.base[t.rank]);
-  for (int q = 0; q < t.nranks; ++q) {
+    WinHeader *me = reinterpret_cast<WinHeader *>(t.base[t.rank]);
     const unsigned long long *p = reduction ? &me->red_arrive[q] : &me->arrive[q];
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < t.epoch) {
@@ -84,19 +84,24 @@ __device__ __forceinline__ void barrier_publish_wait(const PeerTable &t, bool re
       }
     }
   }
+  __syncwarp();
 }
-
 
 // Ends a kernel that wrote into peers' windows: make this CTA's puts visible system-wide, count the CTA, and let the
 // last CTA publish the epoch to every peer and wait for theirs.  Call with all threads of the CTA.
 __device__ __forceinline__ void dist_finish_put(const PeerTable &t, unsigned int nblocks) {
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(t.ctr, 1u);
+  if (threadIdx.x < 32) {           // first warp (every kernel that calls this has >= 32 threads)
+    unsigned int prev = 0;
+    if (threadIdx.x == 0) prev = atomicAdd(t.ctr, 1u);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
     if (prev == nblocks - 1) {
-      *t.ctr = 0;
-      __threadfence_system();
+      if (threadIdx.x == 0) {
+        *t.ctr = 0;
+        __threadfence_system();
+      }
+      __syncwarp();
       barrier_publish_wait(t, false);
     }
   }
