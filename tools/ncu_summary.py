@@ -17,14 +17,21 @@ WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "sm__cycles_elapsed.avg", "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
 
 
 def main(rep, out):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
-    cols = [(w, hdr.index(w)) for w in WANT if w in hdr]
+    cols = []
+    for w in WANT:
+        hit = [i for i, h in enumerate(hdr) if h == w or h.endswith("." + w)]
+        if hit:
+            cols.append((w, hit[0]))
     with open(out, "w", newline="") as fh:
         wr = csv.writer(fh)
         wr.writerow([f"{w} [{units[i]}]" if units[i] else w for w, i in cols])
