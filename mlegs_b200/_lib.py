@@ -65,6 +65,7 @@ _SIGS = {
     "mlegs_b200_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mlegs_b200_host_unregister": (C.c_int, [C.c_void_p]),
     "mlegs_b200_trans": (C.c_int, [_P(Field), C.c_char_p]),
+    "mlegs_b200_trans_many": (C.c_int, [C.c_int, C.c_void_p, C.c_char_p]),
     "mlegs_b200_trans_host": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]),
     "mlegs_b200_trans_host_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p]),
     "mlegs_b200_exchange": (C.c_int, [_P(Field), C.c_int, C.c_int]),

@@ -99,8 +99,10 @@ static int free_all() {
   void *ptrs[] = {c.d_x, c.d_w, c.d_lnx, c.d_r, c.d_lognorm, c.d_pf, c.d_at0, c.d_at1, c.d_ak, c.d_tw_p,
                   c.d_tw_z, c.d_del2h, c.d_xxdx, c.d_vtab, c.d_dtab, c.d_scratch[0], c.d_scratch[1],
                   c.d_scratch[2], c.d_scratch[3], c.d_scratch[4], c.d_scratch[5], c.d_red, c.d_solve_ws, c.d_flags,
-                  c.d_flag, c.d_colstart};
+                  c.d_flag, c.d_colstart, c.d_cossin_p};
   for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (void *p : c.d_batch)
     if (p) cudaFree(p);
   if (c.h_red) cudaFreeHost(c.h_red);
   void *st = c.stream;

@@ -256,13 +256,20 @@ int setup_fft_kernels() {
 
 int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, long long batch0,
                      long long stride_pt, int batch1, long long stride_b1, const double *tw, int tw_order,
-                     double scale, cudaStream_t st) {
+                     double scale, cudaStream_t st, const FieldBatch *fb) {
   if (batch0 <= 0 || batch1 <= 0) return MLEGS_OK;
   static const char *names[4] = {"fft_z_forward", "fft_z_backward", "fft_phi_forward", "fft_phi_backward"};
+  if (fb && fb->n > 0 && !fft_reg_supported(plan.n)) {
+    // lengths outside the register kernels: one launch per scalar
+    for (int i = 0; i < fb->n; ++i)
+      MLEGS_TRY(launch_fft_lines(mode, plan, fb->in[i], fb->out[i], batch0, stride_pt, batch1, stride_b1, tw, tw_order,
+                                 scale, st, nullptr));
+    return MLEGS_OK;
+  }
   if (fft_reg_supported(plan.n)) {
     prof_begin(names[(int)mode], st);
     int rc = launch_fft_reg(mode, plan.n, in, out, batch0 * batch1, batch0, stride_b1, stride_pt, tw, tw_order, scale,
-                            nullptr, 0, 0, st);
+                            nullptr, 0, 0, st, nullptr, 0, fb);
     prof_end(st);
     MLEGS_TRY(rc);
     KERNEL_CHECK();
@@ -312,11 +319,12 @@ int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long ro
 
 int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
                          int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,
-                         cudaStream_t st) {
+                         cudaStream_t st, const FieldBatch *fb) {
   if (nlines <= 0) return MLEGS_OK;
   if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: compact mode needs the register kernels");
   prof_begin(mode == FFT_C2C_FWD ? "fft_z_forward" : "fft_z_backward", st);
-  int rc = launch_fft_reg(mode, plan.n, in, out, nlines, 1, 0, stride_pt, tw, tw_order, scale, colstart, ncols, nrl, st);
+  int rc = launch_fft_reg(mode, plan.n, in, out, nlines, 1, 0, stride_pt, tw, tw_order, scale, colstart, ncols, nrl, st,
+                          nullptr, 0, fb);
   prof_end(st);
   MLEGS_TRY(rc);
   KERNEL_CHECK();

@@ -153,8 +153,8 @@ struct Sched {
 }  // namespace
 
 struct FftRegArgs {
-  const cplx *in;
-  cplx *out;
+  const cplx *in[MLEGS_MAXB];   // one entry per scalar of the launch (blockIdx.y)
+  cplx *out[MLEGS_MAXB];
   long long nlines;      // number of lines handled by this launch
   long long batch0;      // lines q .. with q / batch0 equal are contiguous in memory
   long long stride_b1;   // element offset between such runs
@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
       base = run * a.stride_b1 + (q - run * a.batch0);
     }
   }
-  const cplx *gin = a.in + base;
-  cplx *gout = a.out + base;
+  const cplx *gin = a.in[blockIdx.y] + base;
+  cplx *gout = a.out[blockIdx.y] + base;
   const int tw_unit = a.tw_order / N;   // 1 for c2c; 2 for the real modes (tw_order == 2N)
   const cplx zero = make_double2(0.0, 0.0);
 
@@ -319,7 +319,7 @@ struct RegCfg {
 };
 
 template <int MODE, int N, int E, int THREADS>
-static int launch_one(const FftRegArgs &a, cudaStream_t st) {
+static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
   using C = RegCfg<N, E, THREADS>;
   static bool attr = false;
   if (!attr) {
@@ -327,20 +327,20 @@ static int launch_one(const FftRegArgs &a, cudaStream_t st) {
                                   (int)C::smem));
     attr = true;
   }
-  const unsigned grid = (unsigned)((a.nlines + C::L - 1) / C::L);
+  const dim3 grid((unsigned)((a.nlines + C::L - 1) / C::L), (unsigned)nfields);
   fft_reg_kernel<MODE, N, E, THREADS><<<grid, THREADS, C::smem, st>>>(a);
   return MLEGS_OK;
 }
 
 template <int MODE>
-static int launch_mode(int n, const FftRegArgs &a, cudaStream_t st) {
+static int launch_mode(int n, const FftRegArgs &a, int nfields, cudaStream_t st) {
   switch (n) {
-    case 32: return launch_one<MODE, 32, 8, 256>(a, st);
-    case 64: return launch_one<MODE, 64, 8, 256>(a, st);
-    case 128: return launch_one<MODE, 128, 16, 256>(a, st);
-    case 256: return launch_one<MODE, 256, 16, 256>(a, st);
-    case 512: return launch_one<MODE, 512, 16, 512>(a, st);
-    case 1024: return launch_one<MODE, 1024, 16, 512>(a, st);
+    case 32: return launch_one<MODE, 32, 8, 256>(a, nfields, st);
+    case 64: return launch_one<MODE, 64, 8, 256>(a, nfields, st);
+    case 128: return launch_one<MODE, 128, 16, 256>(a, nfields, st);
+    case 256: return launch_one<MODE, 256, 16, 256>(a, nfields, st);
+    case 512: return launch_one<MODE, 512, 16, 512>(a, nfields, st);
+    case 1024: return launch_one<MODE, 1024, 16, 512>(a, nfields, st);
   }
   return fail(MLEGS_E_ARG, "fft_reg: unsupported length");
 }
@@ -349,13 +349,24 @@ bool fft_reg_supported(int n) { return n == 32 || n == 64 || n == 128 || n == 25
 
 int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
                    long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
-                   const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer, int nrdim) {
+                   const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer, int nrdim,
+                   const FieldBatch *fb) {
   FftRegArgs a;
+  int nfields = 1;
+  if (fb && fb->n > 0) {
+    if (peer) return fail(MLEGS_E_STATE, "fft_reg: the fused exchange handles one scalar per launch");
+    nfields = fb->n;
+    for (int i = 0; i < nfields; ++i) {
+      a.in[i] = fb->in[i];
+      a.out[i] = fb->out[i];
+    }
+  } else {
+    a.in[0] = in;
+    a.out[0] = out;
+  }
   a.use_peer = peer != nullptr;
   a.nrdim = nrdim;
   if (peer) a.pt = *peer;
-  a.in = in;
-  a.out = out;
   a.nlines = nlines;
   a.batch0 = batch0;
   a.stride_b1 = stride_b1;
@@ -367,10 +378,10 @@ int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nli
   a.ncols = ncols;
   a.nrl = nrl;
   switch (mode) {
-    case FFT_C2C_FWD: return launch_mode<FFT_C2C_FWD>(n, a, st);
-    case FFT_C2C_BWD: return launch_mode<FFT_C2C_BWD>(n, a, st);
-    case FFT_R2C_FWD: return launch_mode<FFT_R2C_FWD>(n, a, st);
-    case FFT_C2R_BWD: return launch_mode<FFT_C2R_BWD>(n, a, st);
+    case FFT_C2C_FWD: return launch_mode<FFT_C2C_FWD>(n, a, nfields, st);
+    case FFT_C2C_BWD: return launch_mode<FFT_C2C_BWD>(n, a, nfields, st);
+    case FFT_R2C_FWD: return launch_mode<FFT_R2C_FWD>(n, a, nfields, st);
+    case FFT_C2R_BWD: return launch_mode<FFT_C2R_BWD>(n, a, nfields, st);
   }
   return MLEGS_OK;
 }

@@ -8,6 +8,16 @@ namespace mlegs {
 
 typedef double2 cplx;
 
+// Several independent scalars of identical layout handled by ONE launch (the three components of a vector field,
+// ops:1503-1505; a batch of scalars in mlegs_b200_trans_many): the field index is a grid dimension.
+#define MLEGS_MAXB 8
+struct FieldBatch {
+  int n = 0;
+  const cplx *in[MLEGS_MAXB];
+  cplx *out[MLEGS_MAXB];
+  double ln[MLEGS_MAXB];
+};
+
 // prof.cu: optional CUDA-event timing around each launch
 void prof_begin(const char *name, cudaStream_t st);
 void prof_end(cudaStream_t st);
@@ -20,7 +30,7 @@ int setup_fft_kernels();
 enum FftMode { FFT_C2C_FWD = 0, FFT_C2C_BWD = 1, FFT_R2C_FWD = 2, FFT_C2R_BWD = 3 };
 int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, long long batch0,
                      long long stride_pt, int batch1, long long stride_b1, const double *tw, int tw_order,
-                     double scale, cudaStream_t st);
+                     double scale, cudaStream_t st, const FieldBatch *fb = nullptr);
 
 // fft_reg.cu: register-resident fast path for power-of-two lengths 32..1024
 bool fft_reg_supported(int n);
@@ -28,7 +38,7 @@ struct PeerTable;   // dist_dev.cuh
 int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
                    long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
                    const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer = nullptr,
-                   int nrdim = 0);
+                   int nrdim = 0, const FieldBatch *fb = nullptr);
 // azimuthal r2c FFT whose stores are the exchange(2,1) puts (several ranks, register kernels only)
 int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
                                const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
@@ -36,7 +46,7 @@ int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long ro
 // axial FFT of the retained lines only (rows < nn(m) of each local column); colstart = device prefix sums
 int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
                          int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,
-                         cudaStream_t st);
+                         cudaStream_t st, const FieldBatch *fb = nullptr);
 
 // ---- legendre.cu -----------------------------------------------------------------------
 struct LegArgs {
@@ -57,6 +67,7 @@ struct LegArgs {
   int skip_m0;           // forward only: leave the m == 0 column zero (vec2tp: `if (mv .ne. 0)`)
   const PeerTable *peer; // backward only (host pointer, nullptr on one rank): the stores are the exchange(1,2) puts
   int npdim;             // global number of m columns (fused put addressing)
+  FieldBatch fb;         // fb.n > 0: the launch handles fb.n scalars (in/out/lnval above are ignored)
 };
 int setup_leg_kernels();
 int launch_leg_forward(const LegArgs &a, cudaStream_t st);

@@ -86,16 +86,18 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   FwdSmem &S = *reinterpret_cast<FwdSmem *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int par = warp >> 2, wr = (warp >> 1) & 1, wc = warp & 1;
-  const int ml = blockIdx.z;
+  // scalars of one launch are neighbours in the grid so that they share the table slice of their m in L2
+  const int fld = blockIdx.z % a.fb.n, ml = blockIdx.z / a.fb.n;
   const int mglob = a.m0 + ml;
   const int nn = (a.skip_m0 && mglob == 0) ? 0 : nn_of_m(mglob, a.nrc, a.npc);
   const int n0 = blockIdx.y * LEG_MT_F;
   const int kz0 = blockIdx.x * LEG_NTC;
   const size_t col_stride = (size_t)a.nrl * a.npl;     // elements between z planes
-  const cplx *in = a.in + (size_t)ml * a.nrl;
-  cplx *out = a.out + (size_t)ml * a.nrl;
+  const cplx *in = a.fb.in[fld] + (size_t)ml * a.nrl;
+  cplx *out = a.fb.out[fld] + (size_t)ml * a.nrl;
   const double *pf = a.pf + (size_t)mglob * a.nrh * a.ne;
-  const bool use_ln = (mglob == 0) && (a.lnval != 0.0);
+  const double lnval = a.fb.ln[fld];
+  const bool use_ln = (mglob == 0) && (lnval != 0.0);
   const bool have_w = a.w != nullptr;
   const bool vec2 = (a.nrh & 1) == 0;                  // table rows are 16-byte aligned
 
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
     if (use_ln) {   // log term removed from the real part of the m = 0 column (ops:193-195)
       const int i = c * LEG_KC + k;
       if (i < a.nrh) {
-        l1 = a.lnval * __ldg(&a.lnx[i]);
-        l2 = a.lnval * __ldg(&a.lnx[a.nr - 1 - i]);
+        l1 = lnval * __ldg(&a.lnx[i]);
+        l2 = lnval * __ldg(&a.lnx[a.nr - 1 - i]);
       }
     }
 #pragma unroll
@@ -281,16 +283,17 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a,
   BwdSmem *sm = reinterpret_cast<BwdSmem *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int par = warp >> 2, wr = (warp >> 1) & 1, wc = warp & 1;
-  const int ml = blockIdx.z;
+  const int fld = blockIdx.z % a.fb.n, ml = blockIdx.z / a.fb.n;
   const int mglob = a.m0 + ml;
   const int nn = nn_of_m(mglob, a.nrc, a.npc);
   const int i0 = blockIdx.y * LEG_MT_B;
   const int kz0 = blockIdx.x * LEG_NTC;
   const size_t col_stride = (size_t)a.nrl * a.npl;
-  const cplx *in = a.in + (size_t)ml * a.nrl;
-  cplx *out = a.out + (size_t)ml * a.nrl;
+  const cplx *in = a.fb.in[fld] + (size_t)ml * a.nrl;
+  cplx *out = a.fb.out[fld] + (size_t)ml * a.nrl;
   const double *pf = a.pf + (size_t)mglob * a.nrh * a.ne;
-  const bool use_ln = (mglob == 0) && (a.lnval != 0.0);
+  const double lnval = a.fb.ln[fld];
+  const bool use_ln = (mglob == 0) && (lnval != 0.0);
   const bool vec2 = (a.nrh & 1) == 0;
 
   double acc[4][4][2];
@@ -393,8 +396,8 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a,
       cplx top = make_double2(er + orr, ei + oi);
       cplx bot = make_double2(er - orr, ei - oi);
       if (use_ln) {
-        top.x += a.lnval * __ldg(&a.lnx[ii]);
-        bot.x += a.lnval * __ldg(&a.lnx[a.nr - 1 - ii]);
+        top.x += lnval * __ldg(&a.lnx[ii]);
+        bot.x += lnval * __ldg(&a.lnx[a.nr - 1 - ii]);
       }
       if (PUT) {
         int dq;
@@ -442,12 +445,25 @@ int setup_leg_kernels() {
   return MLEGS_OK;
 }
 
-int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
+// single-scalar callers leave fb.n == 0: the launch then handles in/out/lnval
+static LegArgs with_batch(const LegArgs &a0) {
+  LegArgs a = a0;
+  if (a.fb.n <= 0) {
+    a.fb.n = 1;
+    a.fb.in[0] = a.in;
+    a.fb.out[0] = a.out;
+    a.fb.ln[0] = a.lnval;
+  }
+  return a;
+}
+
+int launch_leg_forward(const LegArgs &a0, cudaStream_t st) {
+  const LegArgs a = with_batch(a0);
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   // row tiles: up to the largest truncation among the local columns (the last tile zero-fills rows beyond it)
   int nn_max = (a.m0 < a.npc) ? std::max(std::min(a.nrc, a.nrc - a.m0), 0) : 0;
   nn_max = std::max(1, std::min(nn_max, a.nrdim));
-  dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (nn_max + LEG_MT_F - 1) / LEG_MT_F, a.npl);
+  dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (nn_max + LEG_MT_F - 1) / LEG_MT_F, a.npl * a.fb.n);
   prof_begin("legendre_forward", st);
   leg_forward_kernel<<<grid, LEG_THREADS, sizeof(FwdSmem), st>>>(a);
   prof_end(st);
@@ -455,9 +471,11 @@ int launch_leg_forward(const LegArgs &a, cudaStream_t st) {
   return MLEGS_OK;
 }
 
-int launch_leg_backward(const LegArgs &a, cudaStream_t st) {
+int launch_leg_backward(const LegArgs &a0, cudaStream_t st) {
+  const LegArgs a = with_batch(a0);
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
-  dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrh + LEG_MT_B - 1) / LEG_MT_B, a.npl);
+  if (a.peer && a.fb.n != 1) return fail(MLEGS_E_STATE, "rtrans_backward: the fused exchange handles one scalar per launch");
+  dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrh + LEG_MT_B - 1) / LEG_MT_B, a.npl * a.fb.n);
   prof_begin(a.peer ? "legendre_backward_put" : "legendre_backward", st);
   if (a.peer) {
     leg_backward_kernel<true><<<grid, LEG_THREADS, 2 * sizeof(BwdSmem), st>>>(a, *a.peer);

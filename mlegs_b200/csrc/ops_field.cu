@@ -14,9 +14,11 @@ namespace mlegs {
 int trans_impl(mlegs_field *s, const char *to);
 int dist_allreduce(double *d_inout, int n);   // dist.cu: sum over ranks, identical result everywhere
 int dist_check_timeout();
-int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst);
+int trans_many_impl(int n, mlegs_field *const *s, const char *to);
+int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb = nullptr);
 struct PeerTable;
-int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer = nullptr);
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer = nullptr,
+            const FieldBatch *fb = nullptr);
 
 static cudaStream_t strm() { return (cudaStream_t)ctx().stream; }
 static size_t nelem(const mlegs_field *f) { return (size_t)f->loc_sz[0] * f->loc_sz[1] * f->loc_sz[2]; }
@@ -668,16 +670,16 @@ int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr,
   ur->nrchop_offset = up->nrchop_offset = 0;
   MLEGS_TRY(chop_impl(ur));
   MLEGS_TRY(chop_impl(up));
-  MLEGS_TRY(trans_impl(ur, "PPP"));
-  MLEGS_TRY(trans_impl(up, "PPP"));
-  size_t ncols = (size_t)ur->loc_sz[1] * ur->loc_sz[2];
-  MLEGS_TRY(launch_rscale((cplx *)ur->e, ur->loc_sz[0], ncols, ur->loc_st[0], c.p.nr, c.d_r, 1, strm()));
-  MLEGS_TRY(launch_rscale((cplx *)up->e, up->loc_sz[0], ncols, up->loc_st[0], c.p.nr, c.d_r, 1, strm()));
   MLEGS_TRY(del2_impl(uz, true));
   MLEGS_TRY(lin(4, uz, nullptr, nullptr, nullptr, -1.0, 0.0, 0.0));
   uz->nrchop_offset = 0;
   MLEGS_TRY(chop_impl(uz));
-  MLEGS_TRY(trans_impl(uz, "PPP"));
+  // the three backward transforms (ops:1503-1505, 1541) are independent: one launch per stage for all of them
+  mlegs_field *comps[3] = {ur, up, uz};
+  MLEGS_TRY(trans_many_impl(3, comps, "PPP"));
+  size_t ncols = (size_t)ur->loc_sz[1] * ur->loc_sz[2];
+  MLEGS_TRY(launch_rscale((cplx *)ur->e, ur->loc_sz[0], ncols, ur->loc_st[0], c.p.nr, c.d_r, 1, strm()));
+  MLEGS_TRY(launch_rscale((cplx *)up->e, up->loc_sz[0], ncols, up->loc_st[0], c.p.nr, c.d_r, 1, strm()));
   return MLEGS_OK;
 }
 
@@ -714,9 +716,19 @@ int vec2tp_impl(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field 
   MLEGS_TRY(launch_rscale((cplx *)up.e, up.loc_sz[0], ncols, up.loc_st[0], c.p.nr, c.d_r, 0, strm()));   // r*up
 
   // ur, uz -> 'PFF' (phi and z spectral, r physical), ops:1357-1363, 1375-1381
-  MLEGS_TRY(trans_impl(&ur, "PFP"));
-  if (has_z) MLEGS_TRY(stage_z(&ur, true, (cplx *)ur.e, (cplx *)ur.e));
+  {   // the three azimuthal FFTs in one launch, then the axial FFTs of ur and uz in one launch
+    mlegs_field *comps[3] = {&ur, &up, &uz};
+    MLEGS_TRY(trans_many_impl(3, comps, "PFP"));
+    if (has_z) {
+      FieldBatch fb;
+      fb.n = 2;
+      fb.in[0] = fb.out[0] = (cplx *)ur.e;
+      fb.in[1] = fb.out[1] = (cplx *)uz.e;
+      MLEGS_TRY(stage_z(&ur, true, nullptr, nullptr, &fb));
+    }
+  }
   set_space3(&ur, "PFF");
+  set_space3(&uz, "PFF");
   // up -> FFF, far-field value, back to 'PFF' (ops:1365-1373)
   MLEGS_TRY(trans_impl(&up, "FFF"));
   std::vector<double> inf(2 * (size_t)up.loc_sz[2]);
@@ -730,9 +742,6 @@ int vec2tp_impl(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field 
   set_space3(&up, "PFF");
   if (owns_m0(&up))
     MLEGS_TRY(launch_col_update((cplx *)up.e, c.p.nr, 1, c.d_x, nullptr, psi->ln, strm()));
-  MLEGS_TRY(trans_impl(&uz, "PFP"));
-  if (has_z) MLEGS_TRY(stage_z(&uz, true, (cplx *)uz.e, (cplx *)uz.e));
-  set_space3(&uz, "PFF");
 
   ur.nrchop_offset = up.nrchop_offset = uz.nrchop_offset = 3;
   ChopIdx ci;

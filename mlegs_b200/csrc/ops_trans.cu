@@ -59,27 +59,31 @@ static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
   return MLEGS_OK;
 }
 
-// One stage, reading `src` and writing `dst` (may be equal for the FFT stages).
-int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+// One stage, reading `src` and writing `dst` (may be equal for the FFT stages).  fb != nullptr: the stage runs on
+// the fb->n scalars of the batch in one launch (all with the layout/metadata of `s`; src/dst are ignored).
+int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb = nullptr);
+int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb) {
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   long long rows = s->loc_sz[0];
   return launch_fft_lines(forward ? FFT_R2C_FWD : FFT_C2R_BWD, c.plan_p, src, dst, rows, rows, s->loc_sz[2],
-                          rows * (long long)s->loc_sz[1], c.d_tw_p, c.p.np, forward ? 1.0 / c.p.np : 1.0, st);
+                          rows * (long long)s->loc_sz[1], c.d_tw_p, c.p.np, forward ? 1.0 / c.p.np : 1.0, st, fb);
 }
 
-int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb = nullptr);
+int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb) {
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   long long plane = (long long)s->loc_sz[0] * s->loc_sz[1];
   return launch_fft_lines(forward ? FFT_C2C_FWD : FFT_C2C_BWD, c.plan_z, src, dst, plane, plane, 1, 0, c.d_tw_z,
-                          c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st);
+                          c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st, fb);
 }
 
 // Axial FFT restricted to the retained lines (rows < nn(m) of every local column m < npc).  Valid when the
 // other lines are known zeros that stay in place (forward, right after rtrans_forward) or are never read
 // again (backward, right before rtrans_backward).
-static int stage_z_compact(const mlegs_field *s, bool forward, const cplx *src, cplx *dst) {
+static int stage_z_compact(const mlegs_field *s, bool forward, const cplx *src, cplx *dst,
+                           const FieldBatch *fb = nullptr) {
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   const int nrc = c.p.nrchop + s->nrchop_offset, npc = c.p.npchop + s->npchop_offset;
@@ -104,16 +108,19 @@ static int stage_z_compact(const mlegs_field *s, bool forward, const cplx *src, 
   }
   long long plane = (long long)s->loc_sz[0] * s->loc_sz[1];
   return launch_fft_z_compact(forward ? FFT_C2C_FWD : FFT_C2C_BWD, c.plan_z, src, dst, c.d_colstart, npl, s->loc_sz[0],
-                              c.cs_total, plane, c.d_tw_z, c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st);
+                              c.cs_total, plane, c.d_tw_z, c.p.nz, forward ? 1.0 / c.p.nz : 1.0, st, fb);
 }
 
-int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer = nullptr);
-int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer) {
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer = nullptr,
+            const FieldBatch *fb = nullptr);
+int stage_r(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const PeerTable *peer,
+            const FieldBatch *fb) {
   LegArgs a;
   MLEGS_TRY(rtrans_args(s, forward ? "rtrans_forward" : "rtrans_backward", &a));
   a.in = src;
   a.out = dst;
   a.peer = peer;
+  if (fb) a.fb = *fb;
   cudaStream_t st = (cudaStream_t)ctx().stream;
   return forward ? launch_leg_forward(a, st) : launch_leg_backward(a, st);
 }
@@ -238,6 +245,131 @@ int trans_impl(mlegs_field *s, const char *to) {
   return MLEGS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// trans() of several scalars at once (one rank): the same state machine, but every stage is ONE launch
+// over all scalars of the batch (field index = a grid dimension).  The scalars must agree in space,
+// chopping offsets and layout -- e.g. the components of a vector field (ops:1503-1505) or the fields of
+// a multi-scalar app.  Arithmetic per scalar is identical to trans_impl (bit-identical results).
+// ------------------------------------------------------------------------------------------------
+static int batch_scratch(int n, cplx **tmp) {
+  Context &c = ctx();
+  static_assert(MLEGS_MAXB <= sizeof(c.d_batch) / sizeof(c.d_batch[0]), "batch scratch");
+  for (int i = 0; i < n; ++i) {   // field-sized, allocated on first use, freed with the context
+    if (!c.d_batch[i]) CUDA_TRY(cudaMalloc(&c.d_batch[i], c.field_bytes));
+    tmp[i] = (cplx *)c.d_batch[i];
+  }
+  return MLEGS_OK;
+}
+
+static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
+  Context &c = ctx();
+  cudaStream_t st = (cudaStream_t)c.stream;
+  const bool has_p = c.p.np > 1, has_z = c.p.nz > 1;
+  const bool compact_ok = has_z && fft_reg_supported(c.plan_z.n);
+  cplx *home[MLEGS_MAXB], *tmp[MLEGS_MAXB];
+  MLEGS_TRY(batch_scratch(n, tmp));
+  for (int i = 0; i < n; ++i) home[i] = (cplx *)s[i]->e;
+  bool at_home = true, rows_zero = false;
+  const mlegs_field *s0 = s[0];
+  // batch reading from where the data is and writing in place (inplace) or to the other buffer
+  auto make = [&](bool inplace, FieldBatch *fb) {
+    fb->n = n;
+    for (int i = 0; i < n; ++i) {
+      cplx *from = at_home ? home[i] : tmp[i];
+      fb->in[i] = from;
+      fb->out[i] = inplace ? from : (at_home ? tmp[i] : home[i]);
+      fb->ln[i] = s[i]->ln;
+    }
+  };
+  FieldBatch fb;
+  if (cur < dst) {   // forward, ops:185-208
+    while (cur < dst) {
+      if (cur == 0 && has_p) {
+        const bool inplace = !(dst >= 2);
+        make(inplace, &fb);
+        MLEGS_TRY(stage_phi(s0, true, nullptr, nullptr, &fb));
+        if (!inplace) at_home = !at_home;
+      } else if (cur == 1) {
+        make(false, &fb);
+        MLEGS_TRY(stage_r(s0, true, nullptr, nullptr, nullptr, &fb));
+        at_home = !at_home;
+        rows_zero = true;
+      } else if (cur == 2 && has_z) {
+        const bool inplace = at_home;   // land at home whenever possible
+        make(inplace, &fb);
+        if (rows_zero && inplace && compact_ok)
+          MLEGS_TRY(stage_z_compact(s0, true, nullptr, nullptr, &fb));
+        else
+          MLEGS_TRY(stage_z(s0, true, nullptr, nullptr, &fb));
+        if (!inplace) at_home = true;
+      }
+      ++cur;
+    }
+  } else {           // backward, ops:210-233
+    while (cur > dst) {
+      if (cur == 3 && has_z) {
+        const bool inplace = !(dst <= 1);
+        make(inplace, &fb);
+        if (dst <= 1 && compact_ok)
+          MLEGS_TRY(stage_z_compact(s0, false, nullptr, nullptr, &fb));
+        else
+          MLEGS_TRY(stage_z(s0, false, nullptr, nullptr, &fb));
+        if (!inplace) at_home = !at_home;
+      } else if (cur == 2) {
+        make(false, &fb);
+        MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, nullptr, &fb));
+        at_home = !at_home;
+      } else if (cur == 1 && has_p) {
+        const bool inplace = at_home;
+        make(inplace, &fb);
+        MLEGS_TRY(stage_phi(s0, false, nullptr, nullptr, &fb));
+        if (!inplace) at_home = true;
+      }
+      --cur;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    set_space(s[i], dst);
+    if (!at_home) {
+      size_t ne = (size_t)s[i]->loc_sz[0] * s[i]->loc_sz[1] * s[i]->loc_sz[2];
+      CUDA_TRY(cudaMemcpyAsync(home[i], tmp[i], ne * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return MLEGS_OK;
+}
+
+int trans_many_impl(int n, mlegs_field *const *s, const char *to) {
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  if (n <= 0) return MLEGS_OK;
+  const int dst = space_id(to);
+  if (dst < 0) return fail(MLEGS_E_ARG, "trans: only taking PPP, PFP, FFP and FFF for spectral transformation");
+  bool uniform = true;
+  for (int i = 0; i < n; ++i) {
+    if (space_id(s[i]->space) < 0)
+      return fail(MLEGS_E_ARG, "trans: scalar space info corrupted (only accepting PPP, PFP, FFP and FFF)");
+    uniform = uniform && space_id(s[i]->space) == space_id(s[0]->space) &&
+              s[i]->nrchop_offset == s[0]->nrchop_offset && s[i]->npchop_offset == s[0]->npchop_offset &&
+              s[i]->nzchop_offset == s[0]->nzchop_offset;
+    for (int j = 0; j < i; ++j)
+      if (s[i]->e == s[j]->e) return fail(MLEGS_E_ARG, "trans_many: the same scalar appears twice");
+  }
+  // several ranks: the exchange windows hold one scalar at a time; mixed states: nothing to share
+  if (c.nranks > 1 || n == 1 || !uniform) {
+    for (int i = 0; i < n; ++i) MLEGS_TRY(trans_impl(s[i], to));
+    return MLEGS_OK;
+  }
+  const int cur = space_id(s[0]->space);
+  if (cur == dst) return MLEGS_OK;
+  {   // precondition checks of rtrans_* once, before anything is launched
+    LegArgs a;
+    MLEGS_TRY(rtrans_args(s[0], cur < dst ? "rtrans_forward" : "rtrans_backward", &a));
+  }
+  for (int i0 = 0; i0 < n; i0 += MLEGS_MAXB)
+    MLEGS_TRY(trans_group(std::min(MLEGS_MAXB, n - i0), s + i0, cur, dst));
+  return MLEGS_OK;
+}
+
 }  // namespace mlegs
 
 using namespace mlegs;
@@ -245,6 +377,8 @@ using namespace mlegs;
 extern "C" {
 
 int mlegs_b200_trans(mlegs_field *s, const char to[3]) { return trans_impl(s, to); }
+
+int mlegs_b200_trans_many(int n, mlegs_field *const *s, const char to[3]) { return trans_many_impl(n, s, to); }
 
 int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], double ln) {
   Context &c = ctx();

@@ -106,6 +106,13 @@ def trans(s: Scalar, space: str):
     check(_l().mlegs_b200_trans(C.byref(s.f), space.encode()))
 
 
+def trans_many(scalars, space: str):
+    """trans() of several scalars in the same state (e.g. the components of a vector field): one launch per stage."""
+    n = len(scalars)
+    ptrs = (C.POINTER(Field) * n)(*[C.pointer(s.f) for s in scalars])
+    check(_l().mlegs_b200_trans_many(n, ptrs, space.encode()))
+
+
 def trans_host(host_e: np.ndarray, from_space: str, to_space: str, ln: float = 0.0):
     """Reference-facing call on a host array (the Fortran s%e): H2D + trans + D2H."""
     assert host_e.flags.f_contiguous and host_e.dtype == np.complex128

@@ -144,3 +144,49 @@ def test_roundtrip_128_config_and_host_entry():
     for got, w in zip(hs, want):
         assert rel_l2(got, w) < TOL
     assert rel_l2(hs[0], ppp) < TOL
+
+
+@pytest.mark.parametrize("case", ["gate2d", "gate3d", "radix35", "cube64"])
+@pytest.mark.parametrize("nf", [2, 3, 11])
+def test_trans_many_is_bit_identical_to_trans(case, nf):
+    """mlegs_b200_trans_many: one launch per stage over all scalars; same arithmetic per scalar as trans()."""
+    kit, ok = _setup(case)
+    es = [random_fff(ok, seed=10 + i) for i in range(nf)]
+    lns = [0.0 if i % 2 == 0 else 0.1 * i for i in range(nf)]
+    single, many = [], []
+    for e, ln in zip(es, lns):
+        for lst in (single, many):
+            s = mb.Scalar("FFF").upload(e)
+            s.ln = ln
+            lst.append(s)
+    for targets in (("PPP", "FFF"), ("FFP", "PFP", "PPP", "PFP", "FFP", "FFF")):
+        for sp in targets:
+            for s in single:
+                mb.trans(s, sp)
+            mb.trans_many(many, sp)
+            for a, b in zip(single, many):
+                assert b.space == sp
+                assert np.array_equal(a.download(), b.download()), (case, nf, sp)
+    # parity against the oracle for one member of the batch
+    for s, e in zip(many, es):
+        s.upload(e)
+    so = mo.Scalar(e=es[1].copy(order="F"), space="FFF", ln=lns[1])
+    mo.trans(so, "PPP", ok)
+    mb.trans_many(many, "PPP")
+    assert rel_l2(many[1].download(), so.e) < TOL
+
+
+def test_trans_many_mixed_states_and_duplicates():
+    kit, ok = _setup("gate3d")
+    a = mb.Scalar("FFF").upload(random_fff(ok, seed=1))
+    b = mb.Scalar("FFF").upload(random_fff(ok, seed=2))
+    want = []
+    for s in (a, b):
+        t = s.copy()
+        mb.trans(t, "PPP")
+        want.append(t.download())
+    mb.trans(b, "FFP")                      # mixed states: falls back to one trans() per scalar
+    mb.trans_many([a, b], "PPP")
+    assert np.array_equal(a.download(), want[0]) and np.array_equal(b.download(), want[1])
+    with pytest.raises(mb.MlegsError, match="same scalar appears twice"):
+        mb.trans_many([a, a], "FFF")

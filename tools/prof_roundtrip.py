@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=128)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--hyperpow", type=int, default=0)
+ap.add_argument("--batch", type=int, default=1, help="scalars per mlegs_b200_trans_many call")
 args = ap.parse_args()
 
 import mlegs_b200 as mb  # noqa: E402
@@ -29,8 +30,14 @@ rng = np.random.default_rng(0)
 e = rng.standard_normal(kit.glb_sz) + 1j * rng.standard_normal(kit.glb_sz)
 s = mb.Scalar("FFF").upload(np.asfortranarray(e))
 mb.chop(s)
-for _ in range(args.reps):
-    mb.trans(s, "PPP")
-    mb.trans(s, "FFF")
+if args.batch > 1:
+    group = [s] + [s.copy() for _ in range(args.batch - 1)]
+    for _ in range(args.reps):
+        mb.trans_many(group, "PPP")
+        mb.trans_many(group, "FFF")
+else:
+    for _ in range(args.reps):
+        mb.trans(s, "PPP")
+        mb.trans(s, "FFF")
 mb.device_sync()
 print("done", mb.launch_count())
