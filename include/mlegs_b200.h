@@ -170,6 +170,39 @@ int mlegs_b200_axpby(mlegs_field *y, double a, const mlegs_field *x, double b);
 /* all(ieee_is_finite(s%e)) -- check_stability, apps/vortical_flow_3d.f90:397-409 */
 int mlegs_b200_is_finite(const mlegs_field *s, int *all_finite);
 
+/* ---- on-device initial conditions / diagnostics of the vortical-flow apps ----------- */
+/* The reference fills a GLOBAL array on every rank and scatters it (`disassemble`); here each rank fills its own
+ * slab in HBM.  s must be in PPP.
+ * s%e(i,j,k) = sum_c ((-exp(-d_c^2)) * mul / div) / (1 - x_i)^2 on both packed azimuthal lanes, d_c the distance of
+ * the collocation point from centre (xo[c], yo[c]); rows >= nr, columns >= np/2 are zero
+ * (apps/vortical_flow_3d.f90:279-294, 305-318).  ran_noise != 0 adds uniform(-1,1)*ran_noise inside r < ell of the
+ * last centre from a counter-based generator (the reference's rand() is clock-seeded, :467-478). */
+int mlegs_b200_gauss_vortices(mlegs_field *s, int ncentres, const double *xo, const double *yo, double mul, double div,
+                              double ran_noise, unsigned long long seed);
+/* uniform_z_fld, apps/vortical_flow_3d.f90:328-351: cmplx(re, im) on the physical points, zero on the padding */
+int mlegs_b200_fill_physical(mlegs_field *s, double re, double im);
+/* qvort_dist_tp, apps/vortical_flow_3d.f90:258-326: psi, chi (FFF in, FFF out) of two q-vortices at x = -2, +2 */
+int mlegs_b200_qvort_dist_tp(mlegs_field *psi, mlegs_field *chi, double q, double ran_noise, unsigned long long seed);
+/* the field of save_vort_mag, apps/vortical_flow_3d.f90:411-447: (wr,wp,wz) = tp2curlvec(psi,chi), vormag = |w| per
+ * azimuthal lane; wr, wp, wz, vormag are PPP scalars supplied by the caller */
+int mlegs_b200_vort_mag(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *wr, mlegs_field *wp,
+                        mlegs_field *wz, mlegs_field *vormag);
+
+/* ---- field I/O in the reference's file formats ---------------------------------------- */
+/* msave_scalar / mload_scalar, submodules/mlegs_scalar_io.f90:6-250.  is_global != 0: ONE file holding the global
+ * array (binary stream: int32 n1,n2,n3 | complex(p8) a | real(p8) ln | int32 x3 chop offsets | character(3) space;
+ * formatted: 1PE24.15E3 records).  The reference assembles the array on rank 0 (dist:70-203) and writes there; here
+ * rank 0 lays the file out and every rank pwrite()s / pread()s its own slab at its byte offsets, so no rank ever
+ * holds the global array.  is_global == 0: one file per rank, `<fn>_<rank>`, with glb_sz/loc_sz/loc_st in front. */
+int mlegs_b200_msave(const mlegs_field *s, const char *fn, int is_binary, int is_global);
+int mlegs_b200_mload(const char *fn, mlegs_field *s, int is_binary, int is_global);
+/* The host halves of the two calls above (no CUDA): write / read the local block `host_e` described by `meta`
+ * (glb_sz, loc_sz, loc_st, ln, offsets, space).  create != 0 creates the file with header and trailer first (rank 0
+ * of a global file; every rank of a per-rank file); the caller orders create before the other ranks' writes. */
+int mlegs_b200_msave_part(const mlegs_field *meta, const void *host_e, const char *fn, int is_binary, int is_global,
+                          int rank, int create);
+int mlegs_b200_mload_part(const char *fn, mlegs_field *meta, void *host_e, int is_binary, int is_global, int rank);
+
 /* ---- multi-GPU (one process per GPU, slab over m) ------------------------------------ */
 /* CUDA-IPC plumbing for the fused FFT+transpose kernels: each rank exports the handle of its
  * exchange window, the host side all-gathers the 64-byte handles (torch.distributed / MPI)

@@ -9,3 +9,4 @@ from .kit import TfmKit, make_params, finalize               # noqa: F401
 from .scalar import *                                         # noqa: F401,F403
 from .scalar import Scalar                                    # noqa: F401
 from . import dist                                            # noqa: F401,E402
+from . import io                                              # noqa: F401,E402

@@ -94,6 +94,15 @@ _SIGS = {
     "mlegs_b200_tp2curlvec": (C.c_int, [_P(Field)] * 5),
     "mlegs_b200_axpby": (C.c_int, [_P(Field), C.c_double, _P(Field), C.c_double]),
     "mlegs_b200_is_finite": (C.c_int, [_P(Field), _P(C.c_int)]),
+    "mlegs_b200_gauss_vortices": (C.c_int, [_P(Field), C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                            C.c_double, C.c_ulonglong]),
+    "mlegs_b200_fill_physical": (C.c_int, [_P(Field), C.c_double, C.c_double]),
+    "mlegs_b200_qvort_dist_tp": (C.c_int, [_P(Field), _P(Field), C.c_double, C.c_double, C.c_ulonglong]),
+    "mlegs_b200_vort_mag": (C.c_int, [_P(Field)] * 6),
+    "mlegs_b200_msave": (C.c_int, [_P(Field), C.c_char_p, C.c_int, C.c_int]),
+    "mlegs_b200_mload": (C.c_int, [C.c_char_p, _P(Field), C.c_int, C.c_int]),
+    "mlegs_b200_msave_part": (C.c_int, [_P(Field), C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mlegs_b200_mload_part": (C.c_int, [C.c_char_p, _P(Field), C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mlegs_b200_dist_window": (C.c_int, [_P(C.c_void_p), _P(C.c_size_t), C.c_void_p]),
     "mlegs_b200_dist_attach": (C.c_int, [C.c_void_p]),
     "mlegs_b200_dist_detach": (C.c_int, []),

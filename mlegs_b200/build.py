@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 # Operators whose results must round like the reference's non-fused Fortran expressions (band matrices,
 # LU pivots, integrator axpys) are compiled without FMA contraction; they are HBM/latency bound anyway.
-PER_FILE_FLAGS = {"elementwise.cu": ["-fmad=false"], "banded.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"elementwise.cu": ["-fmad=false"], "banded.cu": ["-fmad=false"], "appfields.cu": ["-fmad=false"]}
 
 
 def _sources():

@@ -193,6 +193,36 @@ def tp2curlvec(psi, chi, wr, wp, wz):
     check(_l().mlegs_b200_tp2curlvec(C.byref(psi.f), C.byref(chi.f), C.byref(wr.f), C.byref(wp.f), C.byref(wz.f)))
 
 
+def gauss_vortices(s, centres, mul=1.0, div=1.0, ran_noise=0.0, seed=0):
+    """Sum of Gaussian vortices (-exp(-d^2)*mul/div/(1-x)^2) written into the PPP scalar s on the device."""
+    xo = np.ascontiguousarray([c[0] for c in centres], dtype=np.float64)
+    yo = np.ascontiguousarray([c[1] for c in centres], dtype=np.float64)
+    check(_l().mlegs_b200_gauss_vortices(C.byref(s.f), len(centres), xo.ctypes.data_as(C.c_void_p),
+                                         yo.ctypes.data_as(C.c_void_p), mul, div, ran_noise, seed))
+
+
+def fill_physical(s, re, im): check(_l().mlegs_b200_fill_physical(C.byref(s.f), re, im))
+
+
+def qvort_dist_tp(psi, chi, q=1.0, ran_noise=0.0, seed=0):
+    check(_l().mlegs_b200_qvort_dist_tp(C.byref(psi.f), C.byref(chi.f), q, ran_noise, seed))
+
+
+def vort_mag(psi, chi, wr, wp, wz, vormag):
+    check(_l().mlegs_b200_vort_mag(C.byref(psi.f), C.byref(chi.f), C.byref(wr.f), C.byref(wp.f), C.byref(wz.f),
+                                   C.byref(vormag.f)))
+
+
+def msave(s, fn: str, is_binary: bool = False, is_global: bool = True):
+    """msave_scalar (submodules/mlegs_scalar_io.f90:6-115); several ranks fill one global file cooperatively."""
+    check(_l().mlegs_b200_msave(C.byref(s.f), str(fn).encode(), int(is_binary), int(is_global)))
+
+
+def mload(fn: str, s, is_binary: bool = False, is_global: bool = True):
+    """mload_scalar (submodules/mlegs_scalar_io.f90:117-250); every rank reads its own slab."""
+    check(_l().mlegs_b200_mload(str(fn).encode(), C.byref(s.f), int(is_binary), int(is_global)))
+
+
 def axpby(y, a, x, b): check(_l().mlegs_b200_axpby(C.byref(y.f), a, C.byref(x.f), b))
 
 

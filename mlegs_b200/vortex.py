@@ -16,42 +16,28 @@ from .kit import TfmKit
 from .scalar import Scalar
 
 
-def qvort_dist_tp(kit: TfmKit, q: float = 1.0):
-    """apps/vortical_flow_3d.f90:258-326 with ran_noise = 0 (gfortran's random stream is not reproducible)."""
-    p = kit.params
-    nr, nph, nz = p.nr, p.np // 2, p.nz
-    pang = np.array([2.0 * math.acos(-1.0) / p.np * i for i in range(p.np + 1)])
-    out = []
-    for which in (0, 1):
-        glb = np.zeros(kit.glb_sz, dtype=np.complex128, order="F")
-        rr_ = kit.r[:, None]
-        acc = np.zeros((nr, nph), dtype=np.complex128)
-        for xo in (-2, 2):
-            yo = 0
-            pr = pang[0: 2 * nph: 2][None, :]
-            pi_ = pang[1: 2 * nph: 2][None, :]
-            rr = np.sqrt((rr_ * np.cos(pr) - xo) ** 2.0 + (rr_ * np.sin(pr) - yo) ** 2.0)
-            ri = np.sqrt((rr_ * np.cos(pi_) - xo) ** 2.0 + (rr_ * np.sin(pi_) - yo) ** 2.0)
-            den = (1.0 - kit.x[:, None]) ** 2.0
-            if which == 0:
-                acc = acc + (-np.exp(-(rr ** 2.0)) * 2.0 / den + 1j * (-np.exp(-(ri ** 2.0)) * 2.0 / den))
-            else:
-                acc = acc + (-np.exp(-(rr ** 2.0)) / q / den + 1j * (-np.exp(-(ri ** 2.0)) / q / den))
-        glb[:nr, :nph, :nz] = acc[:, :, None]
-        s = Scalar("PPP").upload_global(glb)
-        ms.trans(s, "FFF")
-        ms.idelsqp(s)
-        ms.zeroat1(s)
-        out.append(s)
-    return out[0], out[1]
+def qvort_dist_tp(kit: TfmKit, q: float = 1.0, ran_noise: float = 0.0, seed: int = 0):
+    """apps/vortical_flow_3d.f90:258-326, filled on the device slab by slab (mlegs_b200_qvort_dist_tp); the reference
+    assembles a global array on the host and scatters it."""
+    psi, chi = Scalar("FFF"), Scalar("FFF")
+    ms.qvort_dist_tp(psi, chi, q, ran_noise, seed)
+    return psi, chi
 
 
 def uniform_z_fld(kit: TfmKit, b: float = -0.5) -> Scalar:
     """apps/vortical_flow_3d.f90:328-351."""
-    p = kit.params
-    glb = np.zeros(kit.glb_sz, dtype=np.complex128, order="F")
-    glb[: p.nr, : p.np // 2, : p.nz] = complex(b, b)
-    return Scalar("PPP").upload_global(glb)
+    uz = Scalar("PPP")
+    ms.fill_physical(uz, b, b)
+    return uz
+
+
+def vort_mag(st_or_psi, chi=None) -> Scalar:
+    """The vorticity-magnitude field of save_vort_mag (apps/vortical_flow_3d.f90:411-447), PPP, on the device."""
+    psi = st_or_psi.psi if chi is None else st_or_psi
+    chi = st_or_psi.chi if chi is None else chi
+    wr, wp, wz, mag = (Scalar("PPP") for _ in range(4))
+    ms.vort_mag(psi, chi, wr, wp, wz, mag)
+    return mag
 
 
 @dataclass

@@ -316,3 +316,83 @@ def test_vortex_time_steps_gate_config():
             vortex.step(st, dt)
             mo.vortex_step(sto, ok, dt)
     print("per-step rel-L2 (psi, chi):", errs)
+
+
+@pytest.mark.parametrize("case", ["gate3d", "chopped", "gate2d"])
+def test_on_device_initial_conditions_and_vort_mag(case):
+    """qvort_dist_tp / uniform_z_fld / the save_vort_mag field are filled slab by slab on the
+    device (apps/vortical_flow_3d.f90:258-351, 411-447) and match the oracle's global-array construction."""
+    kit, ok = _setup(case)
+    p = kit.params
+    # the raw physical-space vortex sum (before trans/idelsqp), one and two centres, both amplitude forms
+    for centres, mul, div in (([(-2.0, 0.0), (2.0, 0.0)], 2.0, 1.0), ([(0.5, -0.25)], 1.0, 1.7)):
+        s = mb.Scalar("PPP")
+        mb.gauss_vortices(s, centres, mul=mul, div=div)
+        want = np.zeros(ok.glb_sz, dtype=np.complex128, order="F")
+        pang = np.array([2.0 * mo.PI / p.np * i for i in range(p.np + 1)])
+        nph = p.np // 2
+        acc = np.zeros((p.nr, nph), dtype=np.complex128)
+        r_ = ok.r[:, None]
+        den = (1.0 - ok.x[:, None]) ** 2.0
+        for xo, yo in centres:
+            pr, pi_ = pang[0:2 * nph:2][None, :], pang[1:2 * nph:2][None, :]
+            rr = np.sqrt((r_ * np.cos(pr) - xo) ** 2.0 + (r_ * np.sin(pr) - yo) ** 2.0)
+            ri = np.sqrt((r_ * np.cos(pi_) - xo) ** 2.0 + (r_ * np.sin(pi_) - yo) ** 2.0)
+            acc = acc + (-np.exp(-(rr ** 2.0)) * mul / div / den + 1j * (-np.exp(-(ri ** 2.0)) * mul / div / den))
+        want[:p.nr, :nph, :p.nz] = acc[:, :, None]
+        got = s.download()
+        assert rel_l2(got, want) < TOL, (case, centres)
+        assert np.array_equal(got == 0, want == 0)          # padding rows/columns are exact zeros
+    psi, chi = vortex.qvort_dist_tp(kit, q=1.3)
+    psio, chio = mo.qvort_dist_tp(ok, q=1.3)
+    assert psi.space == "FFF" and chi.space == "FFF"
+    assert rel_l2(psi.download(), psio.e) < TOL and rel_l2(chi.download(), chio.e) < TOL
+    uz = vortex.uniform_z_fld(kit, b=-0.5)
+    assert np.array_equal(uz.download(), mo.uniform_z_fld(ok, b=-0.5).e)
+    # perturbed start: deterministic in (seed), bounded by ran_noise, confined to r < ell of the last centre
+    a, b = mb.Scalar("PPP"), mb.Scalar("PPP")
+    mb.gauss_vortices(a, [(-2.0, 0.0), (2.0, 0.0)], mul=2.0, ran_noise=1e-3, seed=7)
+    mb.gauss_vortices(b, [(-2.0, 0.0), (2.0, 0.0)], mul=2.0, ran_noise=1e-3, seed=7)
+    clean = mb.Scalar("PPP")
+    mb.gauss_vortices(clean, [(-2.0, 0.0), (2.0, 0.0)], mul=2.0)
+    d = a.download() - clean.download()
+    assert np.array_equal(a.download(), b.download())
+    assert 0 < np.max(np.abs(d.real)) <= 1e-3 and np.max(np.abs(d.imag)) <= 1e-3
+    if p.nz > 1:
+        # vorticity magnitude of the q-vortex pair
+        mag = vortex.vort_mag(psi, chi)
+        wro, wpo, wzo = mo.tp2curlvec(psio, chio, ok)
+        want = np.sqrt(wro.e.real ** 2 + wpo.e.real ** 2 + wzo.e.real ** 2) + 1j * np.sqrt(
+            wro.e.imag ** 2 + wpo.e.imag ** 2 + wzo.e.imag ** 2)
+        assert rel_l2(mag.download(), want) < 1e-10
+    with pytest.raises(mb.MlegsError, match="must be in PPP"):
+        mb.gauss_vortices(psi, [(0.0, 0.0)])
+
+
+@pytest.mark.parametrize("binary", [True, False])
+@pytest.mark.parametrize("is_global", [True, False])
+def test_msave_mload_device_roundtrip(tmp_path, binary, is_global):
+    """msave / mload (submodules/mlegs_scalar_io.f90) of a device-resident scalar, with its metadata."""
+    kit, ok = _setup("gate3d")
+    e = random_fff(ok, seed=21)
+    s = mb.Scalar("FFF").upload(e)
+    s.ln = 0.75
+    s.chop_offset(2, 0, 1)
+    fn = str(tmp_path / "fld")
+    mb.msave(s, fn, is_binary=binary, is_global=is_global)
+    t = mb.Scalar("PPP")
+    t.f.loc_sz[:] = s.f.loc_sz[:]      # a per-rank file describes the local block
+    t.f.loc_st[:] = s.f.loc_st[:]
+    mb.mload(fn, t, is_binary=binary, is_global=is_global)
+    assert t.space == "FFF" and t.ln == 0.75 and (t.f.nrchop_offset, t.f.nzchop_offset) == (2, 1)
+    if binary:
+        assert np.array_equal(t.download(), e)
+    else:
+        assert rel_l2(t.download(), e) < 1e-15
+    if binary and is_global:
+        import struct
+        raw = open(fn, "rb").read()
+        assert raw[:12] == struct.pack("<3i", *kit.glb_sz) and raw[-3:] == b"FFF"
+        assert raw[12:12 + e.nbytes] == e.tobytes(order="F")
+    glb = mb.io.assemble(s)
+    assert np.array_equal(glb, e)
