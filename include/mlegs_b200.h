@@ -138,6 +138,9 @@ int mlegs_b200_del2h(mlegs_field *s);                                     /* ops
 int mlegs_b200_del2(mlegs_field *s);                                      /* ops:520-573 */
 int mlegs_b200_idel2(mlegs_field *s, int have_preln, double preln);       /* ops:575-760 */
 int mlegs_b200_ihelm(mlegs_field *s, double alpha);                       /* ops:791-854 */
+/* (del^2 + alpha) s, ops:762-789.  The reference builds the result in a local scalar and drops it (no write-back), so
+ * its helm is a no-op on s; this entry returns the documented operator (the inverse of ihelm). */
+int mlegs_b200_helm(mlegs_field *s, double alpha);
 int mlegs_b200_helmp(mlegs_field *s, int power, double alpha, double beta);   /* ops:856-903 */
 int mlegs_b200_ihelmp(mlegs_field *s, int power, double alpha, double beta);  /* ops:905-1000 */
 
@@ -152,6 +155,11 @@ int mlegs_b200_fefe(mlegs_field *s, const mlegs_field *nl, double dt);    /* ops
 int mlegs_b200_febe(mlegs_field *s, const mlegs_field *nl, double dt);    /* ops:1157-1198 */
 int mlegs_b200_abcn(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl,
                     mlegs_field *nl_p, double dt);                        /* ops:1200-1262 */
+
+/* ops:1096-1155; is_2nd_svis_p != 0: the second argument already is the previous viscous term.  Quirk kept: in the
+ * inviscid branch the reference zeroes svis instead of svis_p (ops:1135). */
+int mlegs_b200_abab(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl_p, double dt,
+                    int is_2nd_svis_p);
 
 /* ---- vector-field operations --------------------------------------------------------- */
 int mlegs_b200_vecprod(mlegs_field *vr, mlegs_field *vp, mlegs_field *vz,

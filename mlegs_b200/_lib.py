@@ -88,6 +88,8 @@ _SIGS = {
     "mlegs_b200_fefe": (C.c_int, [_P(Field), _P(Field), C.c_double]),
     "mlegs_b200_febe": (C.c_int, [_P(Field), _P(Field), C.c_double]),
     "mlegs_b200_abcn": (C.c_int, [_P(Field)] * 4 + [C.c_double]),
+    "mlegs_b200_abab": (C.c_int, [_P(Field)] * 4 + [C.c_double, C.c_int]),
+    "mlegs_b200_helm": (C.c_int, [_P(Field), C.c_double]),
     "mlegs_b200_vecprod": (C.c_int, [_P(Field)] * 6),
     "mlegs_b200_vec2tp": (C.c_int, [_P(Field)] * 5),
     "mlegs_b200_tp2vec": (C.c_int, [_P(Field)] * 5),

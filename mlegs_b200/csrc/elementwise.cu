@@ -320,6 +320,7 @@ int launch_vecprod(cplx *vr, cplx *vp, cplx *vz, const cplx *ur, const cplx *up,
 //   mode 5: y = a*(y + b*(c*x))              (abcn: a*(sh + dt/2*(hv*svis)), ops:1229,1251)
 //   mode 6: out = sp + beta*s2 + alpha*s     (helmp, ops:893)
 //   mode 7: y = y + dt*(x1 + c*x2)           (fefe: s + dt*(nl + hv*svis), ops:1086-1089)
+//   mode 8: y = y + a*(1.5*(x1 + c*x2) - 0.5*(x3 + d*x4))   (abab, ops:1147)
 // ---------------------------------------------------------------------------------------------
 
 __global__ void lincomb_kernel(LinArgs p) {
@@ -357,6 +358,12 @@ __global__ void lincomb_kernel(LinArgs p) {
       case 6: {
         cplx sp = p.x1[idx], s2 = p.x2[idx], s = p.x3[idx];
         o = make_double2((sp.x + p.b * s2.x) + p.a * s.x, (sp.y + p.b * s2.y) + p.a * s.y);
+        break;
+      }
+      case 8: {
+        cplx x1 = p.x1[idx], x2 = p.x2[idx], x3 = p.x3[idx], x4 = p.x4[idx];
+        o = make_double2(y.x + p.a * (1.5 * (x1.x + p.c * x2.x) - 0.5 * (x3.x + p.d * x4.x)),
+                         y.y + p.a * (1.5 * (x1.y + p.c * x2.y) - 0.5 * (x3.y + p.d * x4.y)));
         break;
       }
       default: {

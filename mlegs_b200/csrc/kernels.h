@@ -112,8 +112,8 @@ struct LinArgs {
   int mode;
   size_t n;
   cplx *y;
-  const cplx *x1, *x2, *x3;
-  double a, b, c;
+  const cplx *x1, *x2, *x3, *x4 = nullptr;
+  double a, b, c, d = 0.0;
 };
 int launch_lincomb(const LinArgs &p, cudaStream_t st);
 int launch_rscale(cplx *e, int nrl, size_t ncols, int r0, int nr, const double *r, int divide, cudaStream_t st);

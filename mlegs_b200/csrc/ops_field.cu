@@ -615,6 +615,58 @@ int abcn_impl(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl
   return MLEGS_OK;
 }
 
+// abab, ops:1096-1155.  Quirk Q2 reproduced: the inviscid branch zeroes `svis` twice (ops:1135) and leaves svis_p a
+// plain copy of s_p.
+int abab_impl(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl_p, double dt, int is_2nd_svis_p) {
+  MLEGS_TRY(ready());
+  MLEGS_TRY(check_fff(s));
+  MLEGS_TRY(check_fff(nl));
+  MLEGS_TRY(check_fff(s_p));
+  MLEGS_TRY(check_fff(nl_p));
+  const mlegs_params &p = ctx().p;
+  mlegs_field svis = temp_like(s, 2), svis_p = temp_like(s_p, 3);
+  double fac, fac_p = 1.0;
+  bool zero, zero_p = false;
+  MLEGS_TRY(viscous_term(s, &svis, &fac, &zero));
+  const bool inviscid = (p.hyperpow == 0 && p.visc < 5.0e-14);
+  if (is_2nd_svis_p || inviscid) {
+    MLEGS_TRY(copy_data(&svis_p, s_p));
+  } else {
+    MLEGS_TRY(viscous_term(s_p, &svis_p, &fac_p, &zero_p));
+  }
+  LinArgs a;
+  a.mode = 8;
+  a.n = nelem(s);
+  a.y = (cplx *)s->e;
+  a.x1 = (const cplx *)nl->e;
+  a.x2 = (const cplx *)svis.e;
+  a.x3 = (const cplx *)nl_p->e;
+  a.x4 = (const cplx *)svis_p.e;
+  a.a = dt;
+  a.b = 0.0;
+  a.c = zero ? 1.0 : fac;
+  a.d = fac_p;
+  MLEGS_TRY(launch_lincomb(a, strm()));
+  s->ln = s->ln + dt * (1.5 * (nl->ln + svis.ln) - 0.5 * (nl_p->ln + svis_p.ln));
+  MLEGS_TRY(copy_data(s_p, s));
+  MLEGS_TRY(copy_data(nl_p, nl));
+  return MLEGS_OK;
+}
+
+// helm, ops:762-789: s <- del2(s) + alpha*s, ln <- alpha*ln.  The reference forms this in a local scalar and never
+// returns it (its helm leaves s unchanged); the documented operator is what is provided here.
+int helm_impl(mlegs_field *s, double alpha) {
+  MLEGS_TRY(ready());
+  MLEGS_TRY(require_fff(s));
+  mlegs_field so = temp_like(s, 2);
+  MLEGS_TRY(copy_data(&so, s));
+  MLEGS_TRY(del2_impl(&so, false));
+  const double ln = alpha * s->ln;
+  MLEGS_TRY(lin(0, s, &so, nullptr, nullptr, 1.0, alpha, 0.0));   // s = so + alpha*s
+  s->ln = ln;
+  return MLEGS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // vector-field operations
 // ---------------------------------------------------------------------------------------------
@@ -851,6 +903,11 @@ int mlegs_b200_febe(mlegs_field *s, const mlegs_field *nl, double dt) { return f
 int mlegs_b200_abcn(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl_p, double dt) {
   return abcn_impl(s, s_p, nl, nl_p, dt);
 }
+int mlegs_b200_abab(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl_p, double dt,
+                    int is_2nd_svis_p) {
+  return abab_impl(s, s_p, nl, nl_p, dt, is_2nd_svis_p);
+}
+int mlegs_b200_helm(mlegs_field *s, double alpha) { return helm_impl(s, alpha); }
 int mlegs_b200_vecprod(mlegs_field *vr, mlegs_field *vp, mlegs_field *vz, const mlegs_field *ur,
                        const mlegs_field *up, const mlegs_field *uz) {
   return vecprod_impl(vr, vp, vz, ur, up, uz);

@@ -176,6 +176,13 @@ def abcn(s, s_p, nl, nl_p, dt):
     check(_l().mlegs_b200_abcn(C.byref(s.f), C.byref(s_p.f), C.byref(nl.f), C.byref(nl_p.f), dt))
 
 
+def abab(s, s_p, nl, nl_p, dt, is_2nd_svis_p=False):
+    check(_l().mlegs_b200_abab(C.byref(s.f), C.byref(s_p.f), C.byref(nl.f), C.byref(nl_p.f), dt, int(is_2nd_svis_p)))
+
+
+def helm(s, alpha): check(_l().mlegs_b200_helm(C.byref(s.f), alpha))
+
+
 def vecprod(vr, vp, vz, ur, up, uz):
     check(_l().mlegs_b200_vecprod(C.byref(vr.f), C.byref(vp.f), C.byref(vz.f), C.byref(ur.f), C.byref(up.f),
                                   C.byref(uz.f)))

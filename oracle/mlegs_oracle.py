@@ -1017,6 +1017,39 @@ def abcn(s: Scalar, s_p: Scalar, nl: Scalar, nl_p: Scalar, dt: float, kit: Kit):
             src.nrchop_offset, src.npchop_offset, src.nzchop_offset)
 
 
+def abab(s: Scalar, s_p: Scalar, nl: Scalar, nl_p: Scalar, dt: float, kit: Kit, is_2nd_svis_p: bool = False):
+    """Adams-Bashforth 2 on both terms; ops:1096-1155.  Quirk Q2 is reproduced: in the inviscid branch the reference
+    zeroes `svis` a second time instead of `svis_p` (ops:1135), so svis_p stays a copy of s_p."""
+    _check_fff(s, nl, s_p, nl_p)
+    p = kit.p
+    svis = _viscous_term(s, kit)
+    if is_2nd_svis_p:
+        svis_p = s_p.copy()
+    elif p.hyperpow == 0 and p.visc < 5.0e-14:
+        svis_p = s_p.copy()                      # ops:1135 writes svis%e, not svis_p%e
+    else:
+        svis_p = _viscous_term(s_p, kit)
+    s.e = s.e + dt * (1.5 * (nl.e + svis.e) - 0.5 * (nl_p.e + svis_p.e))
+    s.ln = s.ln + dt * (1.5 * (nl.ln + svis.ln) - 0.5 * (nl_p.ln + svis_p.ln))
+    for dst, src in ((s_p, s), (nl_p, nl)):
+        dst.e = src.e.copy(order="F")
+        dst.ln, dst.space = src.ln, src.space
+        dst.nrchop_offset, dst.npchop_offset, dst.nzchop_offset = (
+            src.nrchop_offset, src.npchop_offset, src.nzchop_offset)
+
+
+def helm(s: Scalar, alpha: float, kit: Kit):
+    """(del^2 + alpha) s; ops:762-789.  The reference computes the result into a local `so` and never hands it back
+    (no `s = so`, no function result), so its helm leaves s untouched apart from the transform to FFF.  This is the
+    documented intent -- s <- del2(s) + alpha*s, ln <- alpha*ln (ops:785-786) -- i.e. the inverse of ihelm."""
+    _require_fff(s, kit)
+    so = s.copy()
+    del2(so, kit)
+    so.e = so.e + alpha * s.e
+    so.ln = alpha * s.ln
+    s.e, s.ln = so.e, so.ln
+
+
 # --------------------------------------------------------------------------- #
 # vector-field operations
 # --------------------------------------------------------------------------- #

@@ -396,3 +396,38 @@ def test_msave_mload_device_roundtrip(tmp_path, binary, is_global):
         assert raw[12:12 + e.nbytes] == e.tobytes(order="F")
     glb = mb.io.assemble(s)
     assert np.array_equal(glb, e)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("inviscid", [False, True])
+def test_abab_and_helm(case, inviscid):
+    """abab (ops:1096-1155, quirk Q2 kept) and helm (ops:762-789, with the write-back)."""
+    over = dict(visc=0.0, hyperpow=0, hypervisc=0.0) if inviscid else {}
+    kit, ok = _setup(case, **over)
+    e, e2 = random_fff(ok, 31), random_fff(ok, 32)
+    n1, n2 = 0.1 * random_fff(ok, 33), 0.1 * random_fff(ok, 34)
+    dt = 1.0e-3
+    for flag in (False, True):
+        s, so = _pair(ok, e, "FFF", 0.1)
+        sp, spo = _pair(ok, e2, "FFF", 0.3)
+        nl, nlo = _pair(ok, n1, "FFF", -0.05)
+        nlp, nlpo = _pair(ok, n2, "FFF", 0.02)
+        for _ in range(2):
+            mb.abab(s, sp, nl, nlp, dt, is_2nd_svis_p=flag)
+            mo.abab(so, spo, nlo, nlpo, dt, ok, is_2nd_svis_p=flag)
+            assert rel_l2(s.download(), so.e) < 1e-10, (case, inviscid, flag)
+            assert np.array_equal(sp.download(), s.download()) and np.array_equal(nlp.download(), nl.download())
+            assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
+    if not inviscid:
+        alpha = -3.7
+        s, so = _pair(ok, e, "FFF", 0.2)
+        mb.helm(s, alpha)
+        mo.helm(so, alpha, ok)
+        assert rel_l2(s.download(), so.e) < TOL and abs(s.ln - so.ln) < 1e-15
+        # helm is the inverse of ihelm on the retained coefficients (unless the Nyquist plane sits in both k ranges
+        # of chop_index and is therefore processed twice by every operator, as in the gate's nzchop = nz/2 + 1)
+        if 2 * kit.params.nzchop <= kit.params.nz:
+            s2, _ = _pair(ok, e, "FFF", 0.0)
+            mb.ihelm(s2, alpha)
+            mb.helm(s2, alpha)
+            assert rel_l2(s2.download(), e) < 1e-9
