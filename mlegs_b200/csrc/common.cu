@@ -92,11 +92,14 @@ int validate_params(const mlegs_params *p) {
 }
 
 int build_operator_tables();   // banded.cu
+int leg_ws_build_pfw();         // legendre_ws.cu
+void leg_ws_reset();
 
 static int free_all() {
   Context &c = ctx();
   band_solve_cache_clear();
-  void *ptrs[] = {c.d_x, c.d_w, c.d_lnx, c.d_r, c.d_lognorm, c.d_pf, c.d_at0, c.d_at1, c.d_ak, c.d_tw_p,
+  leg_ws_reset();
+  void *ptrs[] = {c.d_x, c.d_w, c.d_lnx, c.d_r, c.d_lognorm, c.d_pf, c.d_pfw, c.d_at0, c.d_at1, c.d_ak, c.d_tw_p,
                   c.d_tw_z, c.d_del2h, c.d_xxdx, c.d_vtab, c.d_dtab, c.d_scratch[0], c.d_scratch[1],
                   c.d_scratch[2], c.d_scratch[3], c.d_scratch[4], c.d_scratch[5], c.d_red, c.d_solve_ws, c.d_flags,
                   c.d_flag, c.d_colstart, c.d_cossin_p};
@@ -226,6 +229,7 @@ int mlegs_b200_init(const mlegs_params *p, const double *x, const double *w, con
   if (p->nz > 1) MLEGS_TRY(make_fft_plan(p->nz, 0, &c.plan_z));
   MLEGS_TRY(setup_fft_kernels());
   MLEGS_TRY(setup_leg_kernels());
+  MLEGS_TRY(leg_ws_build_pfw());
 
   c.r_cnt.resize(nranks);
   c.r_off.resize(nranks);

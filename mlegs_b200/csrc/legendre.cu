@@ -18,6 +18,7 @@
 // times the quadrature weight is applied when the B fragments are read.  8 warps: 2 parities x (2 x 2)
 // warp tiles of 32 x 32, 16 DMMA tiles per warp per k-step.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "dist_dev.cuh"
@@ -457,9 +458,14 @@ static LegArgs with_batch(const LegArgs &a0) {
   return a;
 }
 
+bool leg_ws_forward_supported(const LegArgs &a);              // legendre_ws.cu
+int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st);
+
 int launch_leg_forward(const LegArgs &a0, cudaStream_t st) {
   const LegArgs a = with_batch(a0);
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
+  static const bool no_ws = getenv("MLEGS_LEG_NO_WS") != nullptr;   // A/B timing against the cp.async kernel
+  if (!no_ws && leg_ws_forward_supported(a)) return launch_leg_forward_ws(a, st);
   // row tiles: up to the largest truncation among the local columns (the last tile zero-fills rows beyond it)
   int nn_max = (a.m0 < a.npc) ? std::max(std::min(a.nrc, a.nrc - a.m0), 0) : 0;
   nn_max = std::max(1, std::min(nn_max, a.nrdim));
@@ -471,10 +477,15 @@ int launch_leg_forward(const LegArgs &a0, cudaStream_t st) {
   return MLEGS_OK;
 }
 
+bool leg_ws_supported(const LegArgs &a);                      // legendre_ws.cu
+int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st);
+
 int launch_leg_backward(const LegArgs &a0, cudaStream_t st) {
   const LegArgs a = with_batch(a0);
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   if (a.peer && a.fb.n != 1) return fail(MLEGS_E_STATE, "rtrans_backward: the fused exchange handles one scalar per launch");
+  static const bool no_ws = getenv("MLEGS_LEG_NO_WS") != nullptr;   // A/B timing against the cp.async kernel
+  if (!no_ws && leg_ws_supported(a)) return launch_leg_backward_ws(a, st);
   dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrh + LEG_MT_B - 1) / LEG_MT_B, a.npl * a.fb.n);
   prof_begin(a.peer ? "legendre_backward_put" : "legendre_backward", st);
   if (a.peer) {

@@ -1,0 +1,755 @@
+// Warp-specialised, TMA-fed (cp.async.bulk + mbarrier) persistent kernels of the radial mapped-Legendre transform:
+// the production path behind launch_leg_backward / launch_leg_forward (legendre.cu keeps the cp.async kernels for
+// shapes the bulk copies cannot address).  Replaces rtrans_backward / rtrans_forward of
+// /root/reference/src/submodules/mlegs_scalar_ops.f90:1852-2008.
+//
+// Why this shape (profiles/r1 and tools/microbench): one DMMA-issuing warp per SM sub-partition already saturates
+// the FP64 tensor pipe (dmma_shapes.cu: 37.1 TFLOP/s with 4 warps per SM), and the LDS-fed inner loop alone reaches
+// 95 % of it (dmma_loop.cu) -- but a kernel whose warps also compute addresses, issue cp.async, wait for their own
+// loads, meet at a CTA barrier every 16 contraction steps and stage the epilogue through shared memory left the pipe
+// idle half of the time (with the DMMAs removed the remaining skeleton still took 80 % of the time).  So:
+//   * FOUR producer warps per CTA walk a dynamically fetched list of output tiles (heaviest first) and moves whole
+//     rows of the table and of the field with cp.async.bulk (the TMA unit; no per-thread address arithmetic, no
+//     register staging), up to 6 stages ahead, signalling full[stage] through the mbarrier transaction count;
+//   * 8 consumer warps wait on full[stage], run the stage's DMMAs, arrive on empty[stage], and store their
+//     accumulators straight to HBM at the end of a tile.  Every warp accumulates BOTH parities of its rows, so the
+//     parity combination f(i) = be + bo, f(nr-1-i) = be - bo happens in registers and a quarter warp stores 128
+//     contiguous bytes.  There is no CTA-wide barrier after start-up.
+// One persistent CTA per SM (grid = SM count).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "dist_dev.cuh"
+
+namespace mlegs {
+
+#define WS_CONS 256                  // consumer threads
+#define WS_PROD 128                  // producer threads: a bulk copy is a warp-uniform instruction (UBLKCP), so the
+                                     // copies of a warp issue one after the other -- four warps issue four at a time
+#define WS_THREADS (WS_CONS + WS_PROD)
+#define WS_RING 8                    // decoded tiles in flight
+#define WS_KC 16                     // contraction steps per stage
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MB_DONE;\n"
+      "bra MB_WAIT;\n"
+      "MB_DONE:\n"
+      "}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA unit, SASS UBLKCP); bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int ws_nn_of_m(int mglob, int nrc, int npc) {
+  if (mglob >= npc) return 0;
+  int v = min(nrc, nrc - mglob);
+  return v > 0 ? v : 0;
+}
+
+template <int N>
+struct IntK {
+  static constexpr int value = N;
+};
+
+// ------------------------------------------------------------------------------------------------
+// backward (synthesis):  be(i,k) = sum_{n even} pf(i,n,m) a(n,k),  bo likewise over odd n,
+//                        f(i) = be + bo,  f(nr-1-i) = be - bo
+// ------------------------------------------------------------------------------------------------
+// Output tile = 64 rows i x 32 z planes of one column m of one scalar; a stage = 32 consecutive n (16 of each parity):
+// the table rows pf(i0 .. i0+63, n, m) (512 contiguous bytes each) and the coefficient rows a(n .. n+31, kz) of the
+// tile's 32 planes (512 contiguous bytes each).
+#define WSB_MT 64
+#define WSB_NTC 32
+#define WSB_LDA (WSB_MT + 4)            // doubles per table row in shared memory   (fragment reads conflict-free)
+#define WSB_LDB (4 * WS_KC + 2)         // doubles per coefficient row               (idem)
+#define WSB_NS 6
+
+struct BwdStageWS {
+  double A[2][WS_KC][WSB_LDA];          // [parity of n][pair index][i]
+  double B[WSB_NTC][WSB_LDB];           // [kz][n (32 consecutive), (re, im) interleaved]
+};
+struct BwdCtxWS {
+  const double *pf;                     // table slice of this column, at row i0
+  const cplx *in;                       // coefficients a(0, m, kz0)
+  cplx *out;
+  double lnval;
+  int nn, i0, kz0, ml, valid;
+};
+struct BwdSmemWS {
+  BwdStageWS st[WSB_NS];
+  BwdCtxWS ring[WS_RING];
+  unsigned long long full[WSB_NS], empty[WSB_NS];
+};
+static_assert(sizeof(BwdSmemWS) <= 227 * 1024, "shared memory of the backward kernel");
+static_assert((WSB_LDA * 8) % 16 == 0 && (WSB_LDB * 8) % 16 == 0, "bulk copy destinations must be 16-byte aligned");
+
+struct LegItemsB {
+  int total, nkz, nfld, nit, mcount;    // tiles = mcount columns x nfld scalars x nit row tiles x nkz plane tiles
+  unsigned int *ctr;                    // work counter, zeroed before the launch
+};
+
+__device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, BwdCtxWS *cx) {
+  const int it = (int)atomicAdd(L.ctr, 1u);
+  if (it >= L.total) {
+    cx->valid = 0;
+    return;
+  }
+  // kz tile fastest, then row tile, then scalar, then column: concurrent tiles share the table slice of their m in L2
+  const int kzt = it % L.nkz;
+  int rest = it / L.nkz;
+  const int itile = rest % L.nit;
+  rest /= L.nit;
+  const int fld = rest % L.nfld, ml = rest / L.nfld;
+  const int mglob = a.m0 + ml;
+  cx->i0 = itile * WSB_MT;
+  cx->kz0 = kzt * WSB_NTC;
+  cx->pf = a.pf + (size_t)mglob * a.nrh * a.ne + cx->i0;
+  cx->in = a.fb.in[fld] + (size_t)ml * a.nrl + (size_t)cx->kz0 * a.nrl * a.npl;
+  cx->out = a.fb.out[fld] + (size_t)ml * a.nrl;
+  cx->lnval = (mglob == 0) ? a.fb.ln[fld] : 0.0;
+  cx->nn = ws_nn_of_m(mglob, a.nrc, a.npc);
+  cx->ml = ml;
+  cx->valid = 1;
+}
+
+template <bool PUT>
+__global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs a, LegItemsB L, PeerTable pt) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  BwdSmemWS &S = *reinterpret_cast<BwdSmemWS *>(smraw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t col_stride = (size_t)a.nrl * a.npl;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < WSB_NS; ++s) {
+      mbar_init(&S.full[s], WS_PROD);
+      mbar_init(&S.empty[s], WS_CONS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  // stale shared memory may hold NaN patterns: the padding and never-copied tails must at least be finite
+  for (int i = tid; i < (int)(sizeof(BwdStageWS) * WSB_NS / 16); i += WS_THREADS)
+    reinterpret_cast<double2 *>(S.st)[i] = make_double2(0.0, 0.0);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+
+  // rows no tile writes: nr .. nrdim-1 of every column (se = 0, ops:1975-1976) and whole columns with nn(m) == 0
+  {
+    const int ncol = L.nfld * a.npl * a.nzl;
+    for (int col = blockIdx.x * (WS_THREADS / 32) + warp; col < ncol; col += gridDim.x * (WS_THREADS / 32)) {
+      const int kz = col % a.nzl, rest = col / a.nzl;
+      const int ml = rest % a.npl, fld = rest / a.npl;
+      const int first = ws_nn_of_m(a.m0 + ml, a.nrc, a.npc) > 0 ? a.nr : 0;
+      for (int r = first + lane; r < a.nrdim; r += 32) {
+        if (PUT) {
+          int dq;
+          size_t dst;
+          slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, r, ml, kz, &dq,
+                         &dst);
+          reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = make_double2(0.0, 0.0);
+        } else {
+          a.fb.out[fld][(size_t)kz * col_stride + (size_t)ml * a.nrl + r] = make_double2(0.0, 0.0);
+        }
+      }
+    }
+  }
+  // The producer publishes tile jj+1 in the ring before it fills any stage of tile jj, so a consumer that has waited
+  // for the stages of tile jj may read ring[jj+1]; tiles 0 and 1 are published before the start-up barrier.  A
+  // consumer therefore never waits on a stage of a tile that does not exist.
+  if (tid == WS_CONS) {
+    bwd_fetch(a, L, &S.ring[0]);
+    bwd_fetch(a, L, &S.ring[1]);
+  }
+  __syncthreads();   // barriers initialised, stages cleared, first tiles published
+
+  if (warp >= WS_CONS / 32) {
+    // =============================== producer warps ===============================
+    // warp pw moves table rows 8 pw .. 8 pw + 7 (lanes 0-7) and coefficient rows 8 pw .. 8 pw + 7 (lanes 8-15) of a stage
+    const int pw = warp - WS_CONS / 32;
+    const int arow_l = (lane < 8) ? pw * 8 + lane : -1;
+    const int brow_l = (lane >= 8 && lane < 16) ? pw * 8 + lane - 8 : -1;
+    int fetched = 2;
+    auto ensure = [&](int j) {          // ring entries 0 .. j have been written (by the first producer thread)
+      while (fetched <= j) {
+        if (tid == WS_CONS) bwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)]);
+        ++fetched;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PROD) : "memory");
+      }
+    };
+    int g = 0;                          // stage counter over all tiles of this CTA
+    for (int jj = 0;; ++jj) {
+      ensure(jj + 1);
+      const BwdCtxWS x = S.ring[jj & (WS_RING - 1)];
+      if (!x.valid) break;
+      const int nch = ((x.nn + 1) / 2 + WS_KC - 1) / WS_KC;
+      const unsigned arow = (unsigned)min(WSB_MT, a.nrh - x.i0) * 8u;       // bytes of one table row piece
+      const int kz = x.kz0 + brow_l;
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int s = g % WSB_NS;
+        if (g >= WSB_NS) mbar_wait(&S.empty[s], ((g / WSB_NS) + 1) & 1);    // consumers are done with stage use g - NS
+        BwdStageWS &B = S.st[s];
+        const int nbase = c * 2 * WS_KC;
+        const int n = nbase + arow_l;                                       // this lane's table row
+        const int nvalid = min(2 * WS_KC, x.nn - nbase);                    // coefficient rows present in this stage
+        const bool do_a = arow_l >= 0 && n < x.nn;
+        const bool do_b = brow_l >= 0 && kz < a.nzl;
+        unsigned bytes = 0;
+        if (do_a) bytes += arow;
+        if (do_b) bytes += (unsigned)nvalid * 16u;
+        if (nvalid < 2 * WS_KC && do_b) {
+          // coefficients beyond the truncation are not stored anywhere (the axial FFT only carries the retained
+          // rows): they are zeros of the contraction.  Table rows beyond nn(m) then multiply zeros.
+          for (int q = nvalid; q < 2 * WS_KC; ++q) {
+            B.B[brow_l][2 * q] = 0.0;
+            B.B[brow_l][2 * q + 1] = 0.0;
+          }
+        }
+        mbar_arrive_expect_tx(&S.full[s], bytes);
+        if (do_a) bulk_g2s(&B.A[n & 1][(n - nbase) >> 1][0], x.pf + (size_t)n * a.nrh, arow, &S.full[s]);
+        if (do_b) bulk_g2s(&B.B[brow_l][0], x.in + (size_t)brow_l * col_stride + nbase, (unsigned)nvalid * 16u, &S.full[s]);
+      }
+    }
+  } else {
+  // =============================== consumer warps ===============================
+  // warp (h, wq): rows i0 + 32 h .. + 31 (4 tiles of 8), real columns 16 wq .. 16 wq + 15 (2 tiles of 8), both parities
+  const int h = warp >> 2, wq = warp & 3;
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[2][4][2][2];
+
+  int g = 0;
+  for (int jj = 0;; ++jj) {
+    const BwdCtxWS &x = S.ring[jj & (WS_RING - 1)];
+    if (!x.valid) break;
+    const int nn = x.nn, i0 = x.i0, kz0 = x.kz0, ml = x.ml;
+    cplx *outp = x.out;
+    const double lnval = x.lnval;
+    const int kpairs = (nn + 1) / 2;
+    const int nch = (kpairs + WS_KC - 1) / WS_KC;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
+
+    for (int c = 0; c < nch; ++c, ++g) {
+      const int s = g % WSB_NS;
+      mbar_wait(&S.full[s], (g / WSB_NS) & 1);
+      const BwdStageWS &B = S.st[s];
+      const int ksteps = min(WS_KC / 4, (kpairs - c * WS_KC + 3) >> 2);     // pairs beyond the truncation are zeros
+#pragma unroll
+      for (int ks = 0; ks < WS_KC / 4; ++ks) {
+        if (ks >= ksteps) break;
+        const int k = ks * 4 + fk;
+        double af[2][4], bf[2][2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) af[p][mt] = B.A[p][k][h * 32 + mt * 8 + fr];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) bf[p][nt] = B.B[(wq * 16 + nt * 8 + fr) >> 1][2 * (2 * k + p) + (fr & 1)];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(acc[p][mt][nt][0], acc[p][mt][nt][1], af[p][mt], bf[p][nt]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty[s]);
+    }
+
+    // epilogue: thread holds (re, im) of be and bo at row i = i0 + 32 h + 8 mt + lane/4, plane kz0 + 8 wq + 4 nt + lane%4
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int ii = i0 + h * 32 + mt * 8 + fr;
+      double l1 = 0.0, l2 = 0.0;
+      if (__double_as_longlong(lnval) != 0 && ii < a.nrh) {   // + ln term of the m = 0 column (ops:219-221)
+        l1 = lnval * __ldg(&a.lnx[ii]);
+        l2 = lnval * __ldg(&a.lnx[a.nr - 1 - ii]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int kz = kz0 + wq * 8 + nt * 4 + fk;
+        if (ii < a.nrh && kz < a.nzl) {
+          const double er = acc[0][mt][nt][0], ei = acc[0][mt][nt][1];
+          const double orr = acc[1][mt][nt][0], oi = acc[1][mt][nt][1];
+          const cplx top = make_double2(er + orr + l1, ei + oi);
+          const cplx bot = make_double2(er - orr + l2, ei - oi);
+          if (PUT) {
+            int dq;
+            size_t dst;
+            slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, ii, ml, kz, &dq,
+                           &dst);
+            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = top;
+            slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, a.nr - 1 - ii,
+                           ml, kz, &dq, &dst);
+            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = bot;
+          } else {
+            outp[(size_t)kz * col_stride + ii] = top;
+            outp[(size_t)kz * col_stride + (a.nr - 1 - ii)] = bot;
+          }
+        }
+      }
+    }
+  }
+  }   // consumers
+  if (PUT) dist_finish_put(pt, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward (analysis):  a(n,k) = sum_{i<nr/2} [pf(i,n,m) w(i)] * (f(i,k) + (-1)^n f(nr-1-i,k))
+// ------------------------------------------------------------------------------------------------
+// Output tile = 128 consecutive n (64 of each parity) x 32 z planes of one column m of one scalar; a stage = 32
+// radial points i.  The table slice arrives as two TMA tensor boxes (16 i x 128 n, 128-byte swizzle: fragment reads are
+// bank-conflict free without padding); the field rows f(i0.., kz) and their mirrors f(.. nr-1-i0, kz) arrive as 512-byte
+// bulk copies.  The quadrature weight is folded into the table once at start-up (pf*w, resident in HBM), so the parity
+// fold left in the DMMA warps' fragment path is one DADD per B fragment: (top + mirror) feeds the rows of one
+// parity, (top - mirror) the other.
+#define WSF_MT 128
+#define WSF_NTC 32
+#define WSF_KC 32                        // radial points per stage
+#define WSF_LDK (WSF_KC + 4)             // complex elements per field row in shared memory (fragment reads conflict-free)
+#define WSF_NS 3
+
+struct FwdStageWS {
+  double A[2][WSF_MT][16];               // two swizzled TMA boxes: [k / 16][n][k % 16, 16-byte chunks XOR (n & 7)]
+  double T[WSF_NTC][2 * WSF_LDK];        // f(i0 + k, kz), (re, im) interleaved
+  double Bm[WSF_NTC][2 * WSF_LDK];       // f(nr-1-i0-k, kz) at complex index WSF_KC-1-k
+};
+struct FwdCtxWS {
+  const cplx *in;                        // f(0, m, kz0)
+  cplx *out;
+  double lnval;
+  int nn, n0, kz0, mglob, valid;
+};
+struct FwdSmemWS {
+  FwdStageWS st[WSF_NS];
+  FwdCtxWS ring[WS_RING];
+  unsigned long long full[WSF_NS], empty[WSF_NS];
+};
+static_assert(sizeof(FwdSmemWS) <= 227 * 1024, "shared memory of the forward kernel");
+static_assert(sizeof(FwdStageWS) % 1024 == 0, "swizzled boxes need 1024-byte alignment");
+
+#define WS_MAXRT 16
+struct LegItemsF {
+  int total, nkz, nfld, mlo;
+  int start[WS_MAXRT + 1];               // tiles of row tile r are start[r] .. start[r+1]-1
+  unsigned int *ctr;
+};
+
+__device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, FwdCtxWS *cx) {
+  const int it = (int)atomicAdd(L.ctr, 1u);
+  if (it >= L.total) {
+    cx->valid = 0;
+    return;
+  }
+  int r = 0;
+  while (it >= L.start[r + 1]) ++r;
+  const int idx = it - L.start[r];
+  const int kzt = idx % L.nkz, rest = idx / L.nkz;
+  const int fld = rest % L.nfld, ml = L.mlo + rest / L.nfld;
+  const int mglob = a.m0 + ml;
+  cx->kz0 = kzt * WSF_NTC;
+  cx->in = a.fb.in[fld] + (size_t)ml * a.nrl + (size_t)cx->kz0 * a.nrl * a.npl;
+  cx->out = a.fb.out[fld] + (size_t)ml * a.nrl;
+  cx->lnval = (mglob == 0) ? a.fb.ln[fld] : 0.0;
+  cx->nn = ws_nn_of_m(mglob, a.nrc, a.npc);
+  cx->n0 = r * WSF_MT;
+  cx->mglob = mglob;
+  cx->valid = 1;
+}
+
+// 3-D TMA box load: table(i, n, m) -> swizzled shared box
+__device__ __forceinline__ void tma_box3(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+    leg_forward_ws_kernel(LegArgs a, LegItemsF L, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char smraw_f[];
+  FwdSmemWS &S = *reinterpret_cast<FwdSmemWS *>(smraw_f);   // no static shared memory: the window starts 1024-aligned
+  if ((smem_u32(smraw_f) & 1023u) != 0) __trap();           // the swizzled boxes rely on it
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t col_stride = (size_t)a.nrl * a.npl;
+  const int NCH = (a.nrh + WSF_KC - 1) / WSF_KC;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < WSF_NS; ++s) {
+      mbar_init(&S.full[s], WS_PROD);
+      mbar_init(&S.empty[s], WS_CONS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  for (int i = tid; i < (int)(sizeof(FwdStageWS) * WSF_NS / 16); i += WS_THREADS)
+    reinterpret_cast<double2 *>(S.st)[i] = make_double2(0.0, 0.0);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+
+  // rows that no tile writes are zeros (se = 0, ops:1898-1899): [ceil128(nn(m)), nrdim) of every column
+  {
+    const int ncol = L.nfld * a.npl * a.nzl;
+    for (int col = blockIdx.x * (WS_THREADS / 32) + warp; col < ncol; col += gridDim.x * (WS_THREADS / 32)) {
+      const int kz = col % a.nzl, rest = col / a.nzl;
+      const int ml = rest % a.npl, fld = rest / a.npl;
+      const int mglob = a.m0 + ml;
+      const int nn = (a.skip_m0 && mglob == 0) ? 0 : ws_nn_of_m(mglob, a.nrc, a.npc);
+      const int first = min(a.nrdim, (nn + WSF_MT - 1) / WSF_MT * WSF_MT);
+      cplx *o = a.fb.out[fld] + (size_t)kz * col_stride + (size_t)ml * a.nrl;
+      for (int n = first + lane; n < a.nrdim; n += 32) o[n] = make_double2(0.0, 0.0);
+    }
+  }
+  if (tid == WS_CONS) {
+    fwd_fetch(a, L, &S.ring[0]);
+    fwd_fetch(a, L, &S.ring[1]);
+  }
+  __syncthreads();   // barriers initialised, stages cleared, first tiles published (same protocol as the backward kernel)
+
+  if (warp >= WS_CONS / 32) {
+    // =============================== producer warps ===============================
+    // warp pw: field rows (z planes) 8 pw .. 8 pw + 7: lanes 0-7 the top rows, lanes 8-15 the mirror rows; the first
+    // producer thread also issues the two table boxes
+    const int pw = warp - WS_CONS / 32;
+    const int row_l = pw * 8 + (lane & 7);
+    const bool is_top = lane < 8, is_mir = lane >= 8 && lane < 16;
+    int fetched = 2;
+    auto ensure = [&](int j) {
+      while (fetched <= j) {
+        if (tid == WS_CONS) fwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)]);
+        ++fetched;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PROD) : "memory");
+      }
+    };
+    int g = 0;
+    for (int jj = 0;; ++jj) {
+      ensure(jj + 1);
+      const FwdCtxWS x = S.ring[jj & (WS_RING - 1)];
+      if (!x.valid) break;
+      const bool row_ok = (is_top || is_mir) && (x.kz0 + row_l < a.nzl);
+      const cplx *src_col = x.in + (size_t)row_l * col_stride;
+      for (int c = 0; c < NCH; ++c, ++g) {
+        const int s = g % WSF_NS;
+        if (g >= WSF_NS) mbar_wait(&S.empty[s], ((g / WSF_NS) + 1) & 1);
+        FwdStageWS &B = S.st[s];
+        const int i0 = c * WSF_KC;
+        const int cnt = min(WSF_KC, a.nrh - i0);     // radial points of this stage (table columns beyond are TMA zero-fill)
+        unsigned bytes = row_ok ? (unsigned)cnt * 16u : 0u;
+        if (tid == WS_CONS) bytes += 2u * WSF_MT * 16u * 8u;
+        mbar_arrive_expect_tx(&S.full[s], bytes);
+        if (tid == WS_CONS) {
+          tma_box3(&B.A[0][0][0], &tmap, i0, x.n0, x.mglob, &S.full[s]);
+          tma_box3(&B.A[1][0][0], &tmap, i0 + 16, x.n0, x.mglob, &S.full[s]);
+        }
+        if (row_ok) {
+          if (is_top)
+            bulk_g2s(&B.T[row_l][0], src_col + i0, (unsigned)cnt * 16u, &S.full[s]);
+          else
+            bulk_g2s(&B.Bm[row_l][2 * (WSF_KC - cnt)], src_col + (a.nr - i0 - cnt), (unsigned)cnt * 16u, &S.full[s]);
+        }
+      }
+    }
+  } else {
+    // =============================== consumer warps ===============================
+    // warp (h, wq): row tiles t = 2 mt + h (8 rows of each parity = 16 consecutive n), real columns 16 wq .. 16 wq + 15
+    const int h = warp >> 2, wq = warp & 3;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int swap = a.swap_parity;   // 0: even rows contract with the sum fold (eomul), 1: with the difference (oemul)
+    double acc[2][4][2][2];
+
+    // NACT: active row tiles of this warp; SWAP: 0 = even rows contract with the sum fold (eomul), 1 = with the
+    // difference (oemul); LN: remove the log term from the real part of the m = 0 column (ops:193-195)
+    auto compute = [&](auto nact_c, auto swap_c, auto ln_c, const FwdStageWS &B, int i0, double lnval) {
+      constexpr int NACT = decltype(nact_c)::value;
+      constexpr int SWAP = decltype(swap_c)::value;
+      constexpr bool LN = decltype(ln_c)::value != 0;
+#pragma unroll
+      for (int ks = 0; ks < WSF_KC / 4; ++ks) {
+        const int k = ks * 4 + fk;                  // radial point within the stage
+        const int kk = k & 15, box = k >> 4;
+        double af[2][4], bf[2][2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+            if (mt < NACT) {
+              const int nl = 16 * (2 * mt + h) + 2 * fr + p;
+              af[p][mt] = B.A[box][nl][(((kk >> 1) ^ (nl & 7)) << 1) + (kk & 1)];
+            }
+        double l1 = 0.0, l2 = 0.0;
+        if (LN) {
+          const int i = i0 + k;
+          if (i < a.nrh && !(fr & 1)) {             // real columns only
+            l1 = lnval * __ldg(&a.lnx[i]);
+            l2 = lnval * __ldg(&a.lnx[a.nr - 1 - i]);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int col = wq * 16 + nt * 8 + fr;    // real column: plane col / 2, real or imaginary part
+          double t = B.T[col >> 1][2 * k + (col & 1)];
+          double mr = B.Bm[col >> 1][2 * (WSF_KC - 1 - k) + (col & 1)];
+          if (LN) {
+            t -= l1;
+            mr -= l2;
+          }
+          bf[SWAP][nt] = t + mr;
+          bf[SWAP ^ 1][nt] = t - mr;
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+            if (mt < NACT) {
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) dmma884(acc[p][mt][nt][0], acc[p][mt][nt][1], af[p][mt], bf[p][nt]);
+            }
+      }
+    };
+    auto compute_n = [&](auto swap_c, auto ln_c, int nact, const FwdStageWS &B, int i0, double lnval) {
+      switch (nact) {
+        case 4: compute(IntK<4>{}, swap_c, ln_c, B, i0, lnval); break;
+        case 3: compute(IntK<3>{}, swap_c, ln_c, B, i0, lnval); break;
+        case 2: compute(IntK<2>{}, swap_c, ln_c, B, i0, lnval); break;
+        case 1: compute(IntK<1>{}, swap_c, ln_c, B, i0, lnval); break;
+        default: break;
+      }
+    };
+
+    int g = 0;
+    for (int jj = 0;; ++jj) {
+      const FwdCtxWS &x = S.ring[jj & (WS_RING - 1)];
+      if (!x.valid) break;
+      const int nn = x.nn, n0 = x.n0, kz0 = x.kz0;
+      cplx *outp = x.out;
+      const double lnval = x.lnval;
+      const int nact = min(4, max(0, (nn - n0 - 16 * h + 31) >> 5));
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
+      for (int c = 0; c < NCH; ++c, ++g) {
+        const int s = g % WSF_NS;
+        mbar_wait(&S.full[s], (g / WSF_NS) & 1);
+        if (__double_as_longlong(lnval) != 0) {
+          if (swap) compute_n(IntK<1>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
+          else compute_n(IntK<0>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
+        } else {
+          if (swap) compute_n(IntK<1>{}, IntK<0>{}, nact, S.st[s], c * WSF_KC, lnval);
+          else compute_n(IntK<0>{}, IntK<0>{}, nact, S.st[s], c * WSF_KC, lnval);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.empty[s]);
+      }
+      // thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex per parity: rows n, n+1
+      // of one z plane (32 contiguous bytes).  The table boxes carry real values beyond nn(m): those rows are zeros
+      // of the truncated expansion.
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int n = n0 + 2 * ((2 * mt + h) * 8 + fr);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int kz = kz0 + wq * 8 + nt * 4 + fk;
+          if (kz < a.nzl) {
+            cplx *o = outp + (size_t)kz * col_stride + n;
+            if (n < a.nrdim)
+              o[0] = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
+            if (n + 1 < a.nrdim)
+              o[1] = (n + 1 < nn) ? make_double2(acc[1][mt][nt][0], acc[1][mt][nt][1]) : make_double2(0.0, 0.0);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static unsigned int *g_ws_ctr = nullptr;
+static int g_ws_sms = 0;
+static std::map<const double *, CUtensorMap> g_tmaps;   // one tensor map per analysis table of the current kit
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ws_setup() {
+  if (g_ws_ctr) return MLEGS_OK;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&g_ws_sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaMalloc((void **)&g_ws_ctr, 4 * sizeof(unsigned int)));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(BwdSmemWS)));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(BwdSmemWS)));
+  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(FwdSmemWS)));
+  return MLEGS_OK;
+}
+
+// table(i, n, m), i fastest: boxes of 16 i x 128 n x 1 m, 128-byte swizzle, zero fill outside the table
+static int table_tmap(const double *tab, int nrh, int ne, int nm, const CUtensorMap **out) {
+  auto it = g_tmaps.find(tab);
+  if (it == g_tmaps.end()) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) return fail(MLEGS_E_CUDA, "cuTensorMapEncodeTiled is not available");
+      encode = (EncodeTiledFn)fn;
+    }
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)nrh, (cuuint64_t)ne, (cuuint64_t)nm};
+    const cuuint64_t strides[2] = {(cuuint64_t)nrh * 8, (cuuint64_t)nrh * ne * 8};
+    const cuuint32_t box[3] = {16, WSF_MT, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)tab, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MLEGS_E_CUDA, "cuTensorMapEncodeTiled failed for the Legendre table");
+    it = g_tmaps.emplace(tab, tm).first;
+  }
+  *out = &it->second;
+  return MLEGS_OK;
+}
+
+__global__ void pfw_kernel(const double *__restrict__ pf, const double *__restrict__ w, double *__restrict__ out, int nrh,
+                           size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = pf[i] * w[i % nrh];
+}
+
+// pf * w, built once per kit (the reference multiplies the weights into the data of every transform, ops:1903-1907)
+int leg_ws_build_pfw() {
+  Context &c = ctx();
+  const size_t n = (size_t)c.nrh * c.ne * c.p.npchop;
+  CUDA_TRY(cudaMalloc((void **)&c.d_pfw, n * sizeof(double)));
+  pfw_kernel<<<1184, 256, 0, (cudaStream_t)c.stream>>>(c.d_pf, c.d_w, c.d_pfw, c.nrh, n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)c.stream));
+  return MLEGS_OK;
+}
+
+void leg_ws_reset() { g_tmaps.clear(); }
+
+// the bulk copies need 16-byte aligned table rows: nr a multiple of 4
+bool leg_ws_supported(const LegArgs &a) { return (a.nrh & 1) == 0; }
+
+// `a` has its batch filled in (legendre.cu: with_batch)
+int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
+  MLEGS_TRY(ws_setup());
+  LegItemsB L;
+  L.nkz = (a.nzl + WSB_NTC - 1) / WSB_NTC;
+  L.nit = (a.nrh + WSB_MT - 1) / WSB_MT;
+  L.nfld = a.fb.n;
+  L.mcount = 0;
+  for (int ml = 0; ml < a.npl; ++ml) {   // nn(m) is non-increasing in m: the columns with work form a prefix
+    const int m = a.m0 + ml;
+    const int nn = m < a.npc ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
+    if (nn <= 0) break;
+    ++L.mcount;
+  }
+  L.total = L.mcount * L.nfld * L.nit * L.nkz;
+  L.ctr = g_ws_ctr;
+  CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
+  const int grid = std::max(1, std::min(g_ws_sms, std::max(L.total, 1)));
+  prof_begin(a.peer ? "legendre_backward_put" : "legendre_backward", st);
+  if (a.peer) {
+    leg_backward_ws_kernel<true><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
+  } else {
+    PeerTable none;
+    memset(&none, 0, sizeof(none));
+    leg_backward_ws_kernel<false><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, none);
+  }
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+// forward: the table contracted against is a.pf (w == nullptr: the vec2tp projection tables) or pf*w
+bool leg_ws_forward_supported(const LegArgs &a) {
+  Context &c = ctx();
+  if ((a.nrh & 1) != 0) return false;
+  if (a.w != nullptr && !(a.pf == c.d_pf && a.w == c.d_w && c.d_pfw)) return false;
+  return true;
+}
+
+int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
+  Context &c = ctx();
+  MLEGS_TRY(ws_setup());
+  const double *tab = a.w ? c.d_pfw : a.pf;
+  const CUtensorMap *tm = nullptr;
+  MLEGS_TRY(table_tmap(tab, a.nrh, a.ne, c.p.npchop, &tm));
+  // tiles: for every row tile r, the local columns whose truncation reaches into it (nn(m) is non-increasing in m,
+  // so they form a prefix) x scalars x z tiles, numbered heaviest first
+  LegItemsF L;
+  L.nkz = (a.nzl + WSF_NTC - 1) / WSF_NTC;
+  L.nfld = a.fb.n;
+  L.mlo = (a.skip_m0 && a.m0 == 0) ? 1 : 0;
+  L.ctr = g_ws_ctr;
+  auto nn_host = [&](int ml) {
+    const int m = a.m0 + ml;
+    return m < a.npc ? std::min(std::max(std::min(a.nrc, a.nrc - m), 0), a.nrdim) : 0;
+  };
+  if (L.mlo < a.npl && nn_host(L.mlo) > WS_MAXRT * WSF_MT)
+    return fail(MLEGS_E_ARG, "rtrans_forward: more than 2048 radial modes are not supported");
+  int total = 0;
+  L.start[0] = 0;
+  for (int r = 0; r < WS_MAXRT; ++r) {
+    int cnt = 0;
+    for (int ml = L.mlo; ml < a.npl && nn_host(ml) > r * WSF_MT; ++ml) ++cnt;
+    total += cnt * L.nfld * L.nkz;
+    L.start[r + 1] = total;
+  }
+  L.total = total;
+  CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
+  const int grid = std::max(1, std::min(g_ws_sms, std::max(total, 1)));
+  LegArgs b = a;
+  b.pf = tab;
+  prof_begin("legendre_forward", st);
+  leg_forward_ws_kernel<<<grid, WS_THREADS, sizeof(FwdSmemWS), st>>>(b, L, *tm);
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
+}  // namespace mlegs

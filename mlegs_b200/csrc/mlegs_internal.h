@@ -70,6 +70,7 @@ struct Context {
   double *d_x = nullptr, *d_w = nullptr, *d_lnx = nullptr, *d_r = nullptr;
   double *d_lognorm = nullptr;   // (ne, npchop)
   double *d_pf = nullptr;        // (nrh, ne, npchop)
+  double *d_pfw = nullptr;       // pf(i,n,m) * w(i): the analysis table of the TMA-fed Legendre kernel
   double *d_at0 = nullptr, *d_at1 = nullptr, *d_ak = nullptr;
   double *d_tw_p = nullptr;      // np twiddles  exp(-2 pi i j/np), interleaved re,im
   double *d_tw_z = nullptr;      // nz twiddles
