@@ -157,10 +157,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // stale shared memory may hold NaN patterns: the padding and never-copied tails must at least be finite
-  for (int i = tid; i < (int)(sizeof(BwdStageWS) * WSB_NS / 16); i += WS_THREADS)
-    reinterpret_cast<double2 *>(S.st)[i] = make_double2(0.0, 0.0);
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 
   // rows no tile writes: nr .. nrdim-1 of every column (se = 0, ops:1975-1976) and whole columns with nn(m) == 0
   {
@@ -225,6 +221,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
         unsigned bytes = 0;
         if (do_a) bytes += arow;
         if (do_b) bytes += (unsigned)nvalid * 16u;
+        // The consumers run the k-steps up to the last retained pair, rounded up to 4 pairs: table rows in that
+        // range beyond nn(m) are not copied and must not hold stale NaN patterns (they multiply zero coefficients).
+        if (arow_l >= 0 && n >= x.nn && n < nbase + 8 * ((nvalid + 7) >> 3)) {
+          double2 *row = reinterpret_cast<double2 *>(&B.A[n & 1][(n - nbase) >> 1][0]);
+          for (int q = 0; q < WSB_MT / 2; ++q) row[q] = make_double2(0.0, 0.0);
+        }
         if (nvalid < 2 * WS_KC && do_b) {
           // coefficients beyond the truncation are not stored anywhere (the axial FFT only carries the retained
           // rows): they are zeros of the contraction.  Table rows beyond nn(m) then multiply zeros.
@@ -417,9 +419,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  for (int i = tid; i < (int)(sizeof(FwdStageWS) * WSF_NS / 16); i += WS_THREADS)
-    reinterpret_cast<double2 *>(S.st)[i] = make_double2(0.0, 0.0);
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 
   // rows that no tile writes are zeros (se = 0, ops:1898-1899): [ceil128(nn(m)), nrdim) of every column
   {
@@ -474,6 +473,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         if (tid == WS_CONS) {
           tma_box3(&B.A[0][0][0], &tmap, i0, x.n0, x.mglob, &S.full[s]);
           tma_box3(&B.A[1][0][0], &tmap, i0 + 16, x.n0, x.mglob, &S.full[s]);
+        }
+        if (row_ok && cnt < WSF_KC) {
+          // radial points beyond nr/2 meet zero-filled table columns: keep stale NaN patterns out of the products
+          double *row = is_top ? &B.T[row_l][2 * cnt] : &B.Bm[row_l][0];
+          for (int q = 0; q < 2 * (WSF_KC - cnt); ++q) row[q] = 0.0;
         }
         if (row_ok) {
           if (is_top)

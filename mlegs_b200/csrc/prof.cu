@@ -73,7 +73,7 @@ int mlegs_b200_prof_enable(int on) {
 }
 
 // Measured DMMA throughput in TFLOP/s (2 flops per FMA): 16 independent accumulator chains per warp, 8 warps per
-// CTA, 4 CTAs per SM, timed with CUDA events on the library's stream (best of 5, ~2.7 ms each).
+// CTA, 4 CTAs per SM, timed with CUDA events on the library's stream (best of 8 after 12 warm-up launches, ~2.7 ms each).
 int mlegs_b200_dmma_peak(double *tflops) {
   cudaStream_t st = (cudaStream_t)ctx().stream;
   int dev = 0, sms = 0;
@@ -85,9 +85,11 @@ int mlegs_b200_dmma_peak(double *tflops) {
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
   const int iters = 8192, blocks = sms * 4;
-  dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);   // warm-up (clocks ramp up over the first milliseconds)
+  // warm-up: the SM clock takes tens of milliseconds of load to settle at its boost state on a fresh box (a single
+  // warm-up launch read 29.7 TFLOP/s on boxes whose next kernels then ran at 32)
+  for (int rep = 0; rep < 12; ++rep) dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
   double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
+  for (int rep = 0; rep < 8; ++rep) {
     CUDA_TRY(cudaEventRecord(e0, st));
     dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
     CUDA_TRY(cudaEventRecord(e1, st));
