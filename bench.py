@@ -223,9 +223,9 @@ def run_native(args):
             fields.append(s0.copy())
     mb.device_sync()
 
-    # one rank: mlegs_b200_trans_many runs every stage of a group of scalars as one launch (scalar index = a grid
-    # dimension); several ranks: one scalar at a time through the exchange windows
-    nb = max(1, args.batch) if world == 1 else 1
+    # mlegs_b200_trans_many runs every stage of a group of scalars as one launch (scalar index = a grid dimension);
+    # on several ranks the group also shares ONE fused peer-memory exchange (and one barrier) per one-way transform
+    nb = max(1, args.batch)
     groups = [fields[i:i + nb] for i in range(0, len(fields), nb)]
 
     def step():

@@ -14,6 +14,7 @@
 // The tiny all-reduces of the reference (SVV energies ops:117-118, calcat ops:265,302, ln ops:394,657,748)
 // use the same mechanism on the reduction slots and sum in rank order on every rank, so all ranks hold
 // bit-identical results.
+#include <algorithm>
 #include <cstring>
 
 #include "dist_dev.cuh"
@@ -77,7 +78,12 @@ static void fill_table(PeerTable *t) {
   t->nranks = c.nranks;
   t->ctr = g_dist.d_ctr;
   t->flag = c.d_flag;
+  t->fstride = g_dist.fbytes;
 }
+
+// scalars one exchange epoch can carry (mlegs_b200_trans_many on several ranks)
+int dist_window_batch() { return g_dist.attached ? g_dist.wbatch : 1; }
+size_t dist_field_stride() { return g_dist.fbytes; }
 
 bool dist_active() { return ctx().nranks > 1 && g_dist.attached; }
 
@@ -194,7 +200,10 @@ int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   static_assert(sizeof(WinHeader) <= DIST_FLAG_BYTES, "header size");
   if (!c.d_window) {
-    g_dist.wstride = align256(c.field_bytes);
+    // W0/W1 carry up to MLEGS_MAXB scalars per epoch (batched transforms), within 8 GB per rank
+    g_dist.fbytes = align256(c.field_bytes);
+    g_dist.wbatch = (int)std::max<size_t>(1, std::min<size_t>(MLEGS_MAXB, ((size_t)8 << 30) / (2 * g_dist.fbytes)));
+    g_dist.wstride = g_dist.fbytes * g_dist.wbatch;
     size_t total = win_data_offset() + 2 * g_dist.wstride;
     CUDA_TRY(cudaMalloc(&c.d_window, total));
     CUDA_TRY(cudaMemset(c.d_window, 0, win_data_offset()));

@@ -26,7 +26,9 @@ struct DistState {
   void *base[DIST_MAX_RANKS] = {nullptr};           // window base of every rank as mapped here
   unsigned long long epoch = 0, red_epoch = 0;
   unsigned int *d_ctr = nullptr;                    // local CTA counter (last-block detection)
-  size_t wstride = 0;                               // bytes of one W buffer
+  size_t wstride = 0;                               // bytes of one W buffer (wbatch scalars)
+  size_t fbytes = 0;                                // bytes of one scalar's slab inside W
+  int wbatch = 1;                                   // scalars one exchange epoch can carry
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -62,6 +64,7 @@ struct PeerTable {
   int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
   int rank, nranks;
   size_t data_off;      // byte offset of W[parity] inside a window
+  size_t fstride;       // bytes between the scalars of a batched exchange inside W
   unsigned long long epoch;
   unsigned int *ctr;
   int *flag;            // device error flags ([2] = exchange timeout)

@@ -306,11 +306,11 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
 
 int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
                                const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
-                               cudaStream_t st) {
+                               cudaStream_t st, const FieldBatch *fb) {
   if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: the fused exchange needs the register kernels");
   prof_begin("fft_phi_forward_put", st);
   int rc = launch_fft_reg(FFT_R2C_FWD, plan.n, in, nullptr, rows * nz, rows, plane, rows, tw, tw_order, scale, nullptr, 0, 0,
-                          st, &peer, nrdim);
+                          st, &peer, nrdim, fb);
   prof_end(st);
   MLEGS_TRY(rc);
   KERNEL_CHECK();

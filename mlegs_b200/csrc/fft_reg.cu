@@ -282,13 +282,14 @@ __global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
           size_t dst;
           slab_put_index(0, a.pt.rank, a.pt.nranks, a.pt.r_cnt, a.pt.r_off, a.pt.m_cnt, a.pt.m_off, a.nrdim, 0, ii, m,
                          (int)kk, &dq, &dst);
-          reinterpret_cast<cplx *>(reinterpret_cast<char *>(a.pt.base[dq]) + a.pt.data_off)[dst] = val;
+          reinterpret_cast<cplx *>(reinterpret_cast<char *>(a.pt.base[dq]) + a.pt.data_off + blockIdx.y * a.pt.fstride)[dst] =
+              val;
         } else {
           gout[(long long)m * a.stride_pt] = val;
         }
       }
     }
-    if (a.use_peer) dist_finish_put(a.pt, gridDim.x);
+    if (a.use_peer) dist_finish_put(a.pt, gridDim.x * gridDim.y);
     return;
   }
 
@@ -354,7 +355,6 @@ int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nli
   FftRegArgs a;
   int nfields = 1;
   if (fb && fb->n > 0) {
-    if (peer) return fail(MLEGS_E_STATE, "fft_reg: the fused exchange handles one scalar per launch");
     nfields = fb->n;
     for (int i = 0; i < nfields; ++i) {
       a.in[i] = fb->in[i];

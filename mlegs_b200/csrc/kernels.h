@@ -42,7 +42,7 @@ int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nli
 // azimuthal r2c FFT whose stores are the exchange(2,1) puts (several ranks, register kernels only)
 int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
                                const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
-                               cudaStream_t st);
+                               cudaStream_t st, const FieldBatch *fb = nullptr);
 // axial FFT of the retained lines only (rows < nn(m) of each local column); colstart = device prefix sums
 int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
                          int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,

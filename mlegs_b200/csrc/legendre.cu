@@ -483,9 +483,9 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st);
 int launch_leg_backward(const LegArgs &a0, cudaStream_t st) {
   const LegArgs a = with_batch(a0);
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
-  if (a.peer && a.fb.n != 1) return fail(MLEGS_E_STATE, "rtrans_backward: the fused exchange handles one scalar per launch");
   static const bool no_ws = getenv("MLEGS_LEG_NO_WS") != nullptr;   // A/B timing against the cp.async kernel
   if (!no_ws && leg_ws_supported(a)) return launch_leg_backward_ws(a, st);
+  if (a.peer && a.fb.n != 1) return fail(MLEGS_E_STATE, "rtrans_backward: the fused exchange handles one scalar per launch");
   dim3 grid((a.nzl + LEG_NTC - 1) / LEG_NTC, (a.nrh + LEG_MT_B - 1) / LEG_MT_B, a.npl * a.fb.n);
   prof_begin(a.peer ? "legendre_backward_put" : "legendre_backward", st);
   if (a.peer) {

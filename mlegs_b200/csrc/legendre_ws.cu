@@ -103,7 +103,7 @@ struct BwdCtxWS {
   const cplx *in;                       // coefficients a(0, m, kz0)
   cplx *out;
   double lnval;
-  int nn, i0, kz0, ml, valid;
+  int nn, i0, kz0, ml, fld, valid;
 };
 struct BwdSmemWS {
   BwdStageWS st[WSB_NS];
@@ -139,6 +139,7 @@ __device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, 
   cx->lnval = (mglob == 0) ? a.fb.ln[fld] : 0.0;
   cx->nn = ws_nn_of_m(mglob, a.nrc, a.npc);
   cx->ml = ml;
+  cx->fld = fld;
   cx->valid = 1;
 }
 
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
           size_t dst;
           slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, r, ml, kz, &dq,
                          &dst);
-          reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = make_double2(0.0, 0.0);
+          reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off + fld * pt.fstride)[dst] =
+              make_double2(0.0, 0.0);
         } else {
           a.fb.out[fld][(size_t)kz * col_stride + (size_t)ml * a.nrl + r] = make_double2(0.0, 0.0);
         }
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
     if (!x.valid) break;
     const int nn = x.nn, i0 = x.i0, kz0 = x.kz0, ml = x.ml;
     cplx *outp = x.out;
+    const size_t woff = PUT ? pt.data_off + x.fld * pt.fstride : 0;   // this scalar's slab inside the peers' windows
     const double lnval = x.lnval;
     const int kpairs = (nn + 1) / 2;
     const int nch = (kpairs + WS_KC - 1) / WS_KC;
@@ -314,10 +317,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
             size_t dst;
             slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, ii, ml, kz, &dq,
                            &dst);
-            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = top;
+            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + woff)[dst] = top;
             slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, a.nr - 1 - ii,
                            ml, kz, &dq, &dst);
-            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off)[dst] = bot;
+            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + woff)[dst] = bot;
           } else {
             outp[(size_t)kz * col_stride + ii] = top;
             outp[(size_t)kz * col_stride + (a.nr - 1 - ii)] = bot;

@@ -261,47 +261,76 @@ static int batch_scratch(int n, cplx **tmp) {
   return MLEGS_OK;
 }
 
+int dist_window_batch();       // dist.cu
+size_t dist_field_stride();
+
+// One group of at most MLEGS_MAXB scalars (several ranks: at most dist_window_batch()).  Every scalar has a current
+// location (its own buffer, its batch scratch buffer, or -- right after a fused exchange -- its slab of this rank's
+// receive window); stages go out of place whenever that lets the last one land at home.
 static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   const bool has_p = c.p.np > 1, has_z = c.p.nz > 1;
+  const bool multi = c.nranks > 1 && has_p;
   const bool compact_ok = has_z && fft_reg_supported(c.plan_z.n);
-  cplx *home[MLEGS_MAXB], *tmp[MLEGS_MAXB];
+  cplx *home[MLEGS_MAXB], *tmp[MLEGS_MAXB], *at[MLEGS_MAXB];
   MLEGS_TRY(batch_scratch(n, tmp));
-  for (int i = 0; i < n; ++i) home[i] = (cplx *)s[i]->e;
-  bool at_home = true, rows_zero = false;
+  for (int i = 0; i < n; ++i) at[i] = home[i] = (cplx *)s[i]->e;
+  bool rows_zero = false;
   const mlegs_field *s0 = s[0];
-  // batch reading from where the data is and writing in place (inplace) or to the other buffer
+  auto other = [&](int i) { return at[i] == home[i] ? tmp[i] : home[i]; };
+  // batch reading from where the data is and writing in place, or to the buffer the data is not in
   auto make = [&](bool inplace, FieldBatch *fb) {
     fb->n = n;
     for (int i = 0; i < n; ++i) {
-      cplx *from = at_home ? home[i] : tmp[i];
-      fb->in[i] = from;
-      fb->out[i] = inplace ? from : (at_home ? tmp[i] : home[i]);
+      fb->in[i] = at[i];
+      fb->out[i] = inplace ? at[i] : other(i);
       fb->ln[i] = s[i]->ln;
+    }
+  };
+  auto moved = [&](const FieldBatch &fb) {
+    for (int i = 0; i < n; ++i) at[i] = fb.out[i];
+  };
+  // the scalars now live in consecutive slabs of this rank's receive window, in the other slab layout
+  auto landed_in_window = [&](void *landed, bool physical) {
+    for (int i = 0; i < n; ++i) {
+      at[i] = reinterpret_cast<cplx *>(reinterpret_cast<char *>(landed) + (size_t)i * dist_field_stride());
+      field_set_layout(s[i], physical);
     }
   };
   FieldBatch fb;
   if (cur < dst) {   // forward, ops:185-208
     while (cur < dst) {
       if (cur == 0 && has_p) {
-        const bool inplace = !(dst >= 2);
-        make(inplace, &fb);
-        MLEGS_TRY(stage_phi(s0, true, nullptr, nullptr, &fb));
-        if (!inplace) at_home = !at_home;
+        if (multi) {
+          // the FFT's stores ARE the (2,1) exchange of all n scalars: one launch, one barrier
+          PeerTable pt;
+          void *landed = nullptr;
+          MLEGS_TRY(dist_begin_put(&pt, &landed));
+          make(true, &fb);
+          const long long rows = s0->loc_sz[0];
+          MLEGS_TRY(launch_fft_phi_forward_put(c.plan_p, nullptr, rows, s0->loc_sz[2], rows * (long long)s0->loc_sz[1],
+                                               c.d_tw_p, c.p.np, 1.0 / c.p.np, pt, c.nrdim, st, &fb));
+          landed_in_window(landed, false);
+        } else {
+          const bool inplace = !(dst >= 2);
+          make(inplace, &fb);
+          MLEGS_TRY(stage_phi(s0, true, nullptr, nullptr, &fb));
+          moved(fb);
+        }
       } else if (cur == 1) {
         make(false, &fb);
         MLEGS_TRY(stage_r(s0, true, nullptr, nullptr, nullptr, &fb));
-        at_home = !at_home;
+        moved(fb);
         rows_zero = true;
       } else if (cur == 2 && has_z) {
-        const bool inplace = at_home;   // land at home whenever possible
+        const bool inplace = at[0] == home[0];   // land at home whenever possible
         make(inplace, &fb);
         if (rows_zero && inplace && compact_ok)
           MLEGS_TRY(stage_z_compact(s0, true, nullptr, nullptr, &fb));
         else
           MLEGS_TRY(stage_z(s0, true, nullptr, nullptr, &fb));
-        if (!inplace) at_home = true;
+        moved(fb);
       }
       ++cur;
     }
@@ -314,25 +343,37 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
           MLEGS_TRY(stage_z_compact(s0, false, nullptr, nullptr, &fb));
         else
           MLEGS_TRY(stage_z(s0, false, nullptr, nullptr, &fb));
-        if (!inplace) at_home = !at_home;
+        moved(fb);
       } else if (cur == 2) {
-        make(false, &fb);
-        MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, nullptr, &fb));
-        at_home = !at_home;
+        if (multi && dst == 0) {
+          // the epilogue's stores ARE the (1,2) exchange (rows go to the ranks that own them in physical space)
+          PeerTable pt;
+          void *landed = nullptr;
+          MLEGS_TRY(dist_begin_put(&pt, &landed));
+          make(true, &fb);
+          MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, &pt, &fb));
+          landed_in_window(landed, true);
+        } else {
+          make(false, &fb);
+          MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, nullptr, &fb));
+          moved(fb);
+        }
       } else if (cur == 1 && has_p) {
-        const bool inplace = at_home;
+        const bool inplace = at[0] == home[0];
         make(inplace, &fb);
-        MLEGS_TRY(stage_phi(s0, false, nullptr, nullptr, &fb));
-        if (!inplace) at_home = true;
+        if (!inplace)
+          for (int i = 0; i < n; ++i) fb.out[i] = home[i];
+        MLEGS_TRY(stage_phi(s[0], false, nullptr, nullptr, &fb));
+        moved(fb);
       }
       --cur;
     }
   }
   for (int i = 0; i < n; ++i) {
     set_space(s[i], dst);
-    if (!at_home) {
+    if (at[i] != home[i]) {
       size_t ne = (size_t)s[i]->loc_sz[0] * s[i]->loc_sz[1] * s[i]->loc_sz[2];
-      CUDA_TRY(cudaMemcpyAsync(home[i], tmp[i], ne * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(home[i], at[i], ne * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
     }
   }
   return MLEGS_OK;
@@ -354,19 +395,30 @@ int trans_many_impl(int n, mlegs_field *const *s, const char *to) {
     for (int j = 0; j < i; ++j)
       if (s[i]->e == s[j]->e) return fail(MLEGS_E_ARG, "trans_many: the same scalar appears twice");
   }
-  // several ranks: the exchange windows hold one scalar at a time; mixed states: nothing to share
-  if (c.nranks > 1 || n == 1 || !uniform) {
+  // mixed states: nothing to share
+  if (n == 1 || !uniform) {
     for (int i = 0; i < n; ++i) MLEGS_TRY(trans_impl(s[i], to));
     return MLEGS_OK;
   }
   const int cur = space_id(s[0]->space);
   if (cur == dst) return MLEGS_OK;
+  int group = MLEGS_MAXB;
+  if (c.nranks > 1 && c.p.np > 1) {
+    // several ranks: the fused exchanges carry dist_window_batch() scalars per epoch; paths that need the stand-alone
+    // exchange (odd lengths, a backward transform that starts at PFP) go one scalar at a time
+    const bool crosses = (cur == 0 && dst >= 1) || (dst == 0 && cur >= 1);
+    const bool fused_ok = fft_reg_supported(c.plan_p.n) && (c.nrh % 2 == 0) && !(dst == 0 && cur == 1);
+    group = std::min(group, dist_window_batch());
+    if (crosses && (!fused_ok || group < 2)) {
+      for (int i = 0; i < n; ++i) MLEGS_TRY(trans_impl(s[i], to));
+      return MLEGS_OK;
+    }
+  }
   {   // precondition checks of rtrans_* once, before anything is launched
     LegArgs a;
     MLEGS_TRY(rtrans_args(s[0], cur < dst ? "rtrans_forward" : "rtrans_backward", &a));
   }
-  for (int i0 = 0; i0 < n; i0 += MLEGS_MAXB)
-    MLEGS_TRY(trans_group(std::min(MLEGS_MAXB, n - i0), s + i0, cur, dst));
+  for (int i0 = 0; i0 < n; i0 += group) MLEGS_TRY(trans_group(std::min(group, n - i0), s + i0, cur, dst));
   return MLEGS_OK;
 }
 

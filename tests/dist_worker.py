@@ -87,6 +87,23 @@ def run_case(nr, np_, nz, nrc, npc, nzc, ell, hp, rank, world, steps):
             mo.trans(so, sp, ok)
             check(f"trans -> {sp} (ln={ln})", s, so.e)
 
+    # ---- batched transforms: one fused exchange for the whole group, bit-identical to one scalar at a time ----
+    seeds = (11, 12, 13)
+    group = [mb.Scalar("FFF").upload_global(random_fff(ok, seed=sd)) for sd in seeds]
+    single = [mb.Scalar("FFF").upload_global(random_fff(ok, seed=sd)) for sd in seeds]
+    for q, g1 in enumerate(group):
+        g1.ln = single[q].ln = 0.1 * q
+    for sp in ("PPP", "FFF", "PFP", "PPP", "FFP", "FFF"):
+        mb.trans_many(group, sp)
+        for s1 in single:
+            mb.trans(s1, sp)
+        for q, (g1, s1) in enumerate(zip(group, single)):
+            assert g1.space == sp and list(g1.loc_sz) == list(s1.loc_sz)
+            same = np.array_equal(g1.download(), s1.download())
+            assert same, f"trans_many -> {sp}: scalar {q} differs from trans()"
+    if rank == 0:
+        print("  trans_many == trans (bit-identical) through PPP/FFF/PFP/PPP/FFP/FFF", flush=True)
+
     # ---- operators with cross-rank reductions ----
     s = mb.Scalar("FFF").upload_global(e0)
     so = mo.Scalar(e=e0.copy(order="F"), space="FFF")
