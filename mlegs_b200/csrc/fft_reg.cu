@@ -10,6 +10,8 @@
 // in memory (the radial index is the fastest one), so global accesses are coalesced 16-byte vectors and
 // every element is read once and written once.  All E loads of a thread are issued before the first
 // butterfly (memory-level parallelism = E x 16 B per thread).
+#include <algorithm>
+
 #include "dist_dev.cuh"
 
 namespace mlegs {
@@ -172,15 +174,14 @@ struct FftRegArgs {
 };
 
 // MODE: FFT_C2C_FWD / FFT_C2C_BWD / FFT_R2C_FWD / FFT_C2R_BWD (kernels.h).
+// one tile = L lines of one scalar (blockIdx.y); `blk` = tile index
 template <int MODE, int N, int E, int THREADS>
-__global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
+__device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long long blk) {
   constexpr int T = N / E, L = THREADS / T;
   using S = Sched<N, E>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx *sm = reinterpret_cast<cplx *>(smem_raw);
   const int tid = threadIdx.x;
   const int l = tid % L, t = tid / L;
-  const long long q = (long long)blockIdx.x * L + l;
+  const long long q = blk * L + l;
   const bool ok = q < a.nlines;
   long long base = 0;
   if (ok) {
@@ -289,7 +290,6 @@ __global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
         }
       }
     }
-    if (a.use_peer) dist_finish_put(a.pt, gridDim.x * gridDim.y);
     return;
   }
 
@@ -311,6 +311,22 @@ __global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
   }
 }
 
+template <int MODE, int N, int E, int THREADS>
+__global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+  constexpr int L = THREADS / (N / E);
+  const long long ntiles = (a.nlines + L - 1) / L;
+  // plain launches have one tile per CTA; the fused exchange runs a grid-stride loop so that the system-scope fence
+  // that ends it (an NVLink round trip during which the CTA still holds its SM resources) is paid once per CTA,
+  // not once per tile
+  for (long long blk = blockIdx.x; blk < ntiles; blk += gridDim.x) {
+    fft_reg_tile<MODE, N, E, THREADS>(a, sm, blk);
+    if (blk + gridDim.x < ntiles) __syncthreads();   // the tile's shared buffer is reused
+  }
+  if (MODE == FFT_R2C_FWD && a.use_peer) dist_finish_put(a.pt, gridDim.x * gridDim.y);
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 
 template <int N, int E, int THREADS>
@@ -328,7 +344,20 @@ static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
                                   (int)C::smem));
     attr = true;
   }
-  const dim3 grid((unsigned)((a.nlines + C::L - 1) / C::L), (unsigned)nfields);
+  long long ntiles = (a.nlines + C::L - 1) / C::L;
+  if (a.use_peer) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      CUDA_TRY(cudaGetDevice(&dev));
+      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int per_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_reg_kernel<MODE, N, E, THREADS>, THREADS, C::smem));
+    const long long resident = (long long)sms * std::max(per_sm, 1);
+    ntiles = std::min(ntiles, std::max(1ll, resident / nfields));
+  }
+  const dim3 grid((unsigned)ntiles, (unsigned)nfields);
   fft_reg_kernel<MODE, N, E, THREADS><<<grid, THREADS, C::smem, st>>>(a);
   return MLEGS_OK;
 }
