@@ -31,6 +31,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "transform_roundtrip_gdofs"
 UNIT = "GDOF/s"
+# measured peer-copy bandwidth per direction per GPU on this pool (B200_PROFILING.md; nominal 900 GB/s)
+NVLINK_PEER_GBPS = 770.0
 
 
 def workload(size: int, world: int = 1, weak: str = "nz"):
@@ -307,6 +309,11 @@ def run_native(args):
         if k.startswith("legendre"):
             ent["TFLOPs"] = per_launch * leg_flops / world / (avg_ms * 1e-3) / 1e12
             ent["fp64_tensor_frac"] = ent["TFLOPs"] / dmma_peak
+        if k.endswith("_put") or k.startswith("exchange"):
+            # the kernel's stores are the all-to-all: (world-1)/world of this rank's slab of every scalar crosses NVLink
+            nv_bytes = per_launch * 16 * nrdim * npdim * nz / world * (world - 1) / world
+            ent["nvlink_GBps"] = nv_bytes / (avg_ms * 1e-3) / 1e9
+            ent["nvlink_frac"] = ent["nvlink_GBps"] / NVLINK_PEER_GBPS
         kernels[k] = ent
     dom = max(prof, key=lambda k: prof[k]["ms"])
     d = kernels[dom]

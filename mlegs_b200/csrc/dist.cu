@@ -45,6 +45,49 @@ __global__ void __launch_bounds__(256) exchange_put_kernel(PeerTable t, const cp
   dist_finish_put(t, gridDim.x);
 }
 
+// Second half of the staged (1,2) exchange: the Legendre synthesis left every scalar's rows in a local staging buffer in
+// destination order (slab_stage_index); this kernel ships them -- per (scalar, peer, plane) one contiguous run of
+// m_cnt[me] * r_cnt[q] elements, 16 bytes per lane, whole warps on consecutive addresses -- and ends with the exchange
+// barrier.  Rank `me` starts with peer me+1, so at any moment the ranks target different peers.
+struct ShipSrc {
+  const cplx *p[MLEGS_MAXB];
+};
+__global__ void __launch_bounds__(256) slab_ship_kernel(PeerTable t, ShipSrc src, int nfld, int nz, int npdim) {
+  const int me = t.rank, P = t.nranks, mc = t.m_cnt[me];
+  const long long nruns = (long long)nfld * P * nz;
+  for (long long run = blockIdx.x; run < nruns; run += gridDim.x) {
+    const int k = (int)(run % nz);
+    const long long rest = run / nz;
+    const int q = (int)((me + 1 + rest % P) % P);
+    const int fld = (int)(rest / P);
+    const int len = mc * t.r_cnt[q];
+    const cplx *s = src.p[fld] + (size_t)t.r_off[q] * mc * nz + (size_t)k * len;
+    cplx *d = reinterpret_cast<cplx *>(reinterpret_cast<char *>(t.base[q]) + t.data_off + fld * t.fstride) +
+              ((size_t)k * npdim + t.m_off[me]) * t.r_cnt[q];
+    for (int e = threadIdx.x; e < len; e += blockDim.x) d[e] = s[e];
+  }
+  dist_finish_put(t, gridDim.x);
+}
+
+int launch_slab_ship(const PeerTable &t, const FieldBatch &fb, cudaStream_t st) {
+  Context &c = ctx();
+  ShipSrc src;
+  for (int i = 0; i < fb.n; ++i) src.p[i] = fb.out[i];
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long nruns = (long long)fb.n * c.nranks * c.nzdim;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(nruns, (long long)sms * 8));
+  prof_begin("exchange_12_ship", st);
+  slab_ship_kernel<<<grid, 256, 0, st>>>(t, src, fb.n, c.nzdim, c.npdim);
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
 // sum over ranks of `n` doubles, in rank order, result on every rank (one CTA)
 __global__ void allreduce_small_kernel(PeerTable t, double *inout, int n, size_t red_off) {
   for (int q = 0; q < t.nranks; ++q) {

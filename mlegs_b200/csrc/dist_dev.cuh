@@ -59,6 +59,16 @@ __host__ __device__ inline void slab_put_index(int dir, int me, int nranks, cons
   *q_out = q;
 }
 
+// Staged (1,2) exchange: element (i, j, k) of the local (nrdim, m_cnt[me], nz) block inside a LOCAL staging buffer laid
+// out in destination order -- one region per owning rank q, each region exactly the piece of q's new block this rank
+// contributes ((r_cnt[q], m_cnt[me]) per plane), so that shipping it is nz contiguous runs per peer.
+__host__ __device__ inline size_t slab_stage_index(int me, int nranks, const int *r_cnt, const int *r_off, const int *m_cnt,
+                                                   int nz, int i, int j, int k) {
+  int q = 0;
+  while (q + 1 < nranks && i >= r_off[q + 1]) ++q;
+  return (size_t)r_off[q] * m_cnt[me] * nz + ((size_t)k * m_cnt[me] + j) * r_cnt[q] + (i - r_off[q]);
+}
+
 struct PeerTable {
   void *base[DIST_MAX_RANKS];
   int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];

@@ -143,8 +143,14 @@ __device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, 
   cx->valid = 1;
 }
 
-template <bool PUT>
+// MODE 0: rows stored in place (i, m, kz).  MODE 1 (several ranks): rows stored straight into the windows of the ranks
+// that own them in physical space (exchange(1,2) fused into the epilogue) + the exchange barrier.  MODE 2: rows stored
+// into the LOCAL output buffer in destination order (slab_stage_index); dist.cu's ship kernel then moves them as long
+// contiguous runs -- at 8 ranks the direct puts are 128-byte pieces and reach a third of the NVLink rate.
+template <int MODE>
 __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs a, LegItemsB L, PeerTable pt) {
+  constexpr bool PUT = MODE == 1;
+  constexpr bool STAGE = MODE == 2;
   extern __shared__ __align__(128) unsigned char smraw[];
   BwdSmemWS &S = *reinterpret_cast<BwdSmemWS *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -173,6 +179,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
           slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, r, ml, kz, &dq,
                          &dst);
           reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off + fld * pt.fstride)[dst] =
+              make_double2(0.0, 0.0);
+        } else if (STAGE) {
+          a.fb.out[fld][slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, r, ml, kz)] =
               make_double2(0.0, 0.0);
         } else {
           a.fb.out[fld][(size_t)kz * col_stride + (size_t)ml * a.nrl + r] = make_double2(0.0, 0.0);
@@ -321,6 +330,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
             slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, a.nr - 1 - ii,
                            ml, kz, &dq, &dst);
             reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + woff)[dst] = bot;
+          } else if (STAGE) {
+            cplx *base = outp - (size_t)ml * a.nrl;   // start of this scalar's staging buffer
+            base[slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, ii, ml, kz)] = top;
+            base[slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, a.nr - 1 - ii, ml, kz)] = bot;
           } else {
             outp[(size_t)kz * col_stride + ii] = top;
             outp[(size_t)kz * col_stride + (a.nr - 1 - ii)] = bot;
@@ -367,33 +380,41 @@ struct FwdSmemWS {
 static_assert(sizeof(FwdSmemWS) <= 227 * 1024, "shared memory of the forward kernel");
 static_assert(sizeof(FwdStageWS) % 1024 == 0, "swizzled boxes need 1024-byte alignment");
 
-#define WS_MAXRT 16
+// Tile order: row tile fastest, then z tile, then scalar, then column m (heaviest columns first).  The row tiles of one
+// (m, scalar, z tile) read the same field rows and run at the same time on neighbouring SMs, so the field is fetched
+// from HBM once and the other row tiles hit in L2 (at 512^3 the row-tile-major order re-read it 4x: ncu 4.0 GB
+// against 1.1 GB); the table slice of (m, row tile) is shared by the z tiles and scalars that follow within the
+// same few hundred tiles.  Row tiles beyond the truncation of their column are skipped at fetch time.
 struct LegItemsF {
-  int total, nkz, nfld, mlo;
-  int start[WS_MAXRT + 1];               // tiles of row tile r are start[r] .. start[r+1]-1
+  int total, nkz, nfld, mlo, nrt;        // nrt = row tiles of the widest column
   unsigned int *ctr;
 };
 
 __device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, FwdCtxWS *cx) {
-  const int it = (int)atomicAdd(L.ctr, 1u);
-  if (it >= L.total) {
-    cx->valid = 0;
+  for (;;) {
+    const int it = (int)atomicAdd(L.ctr, 1u);
+    if (it >= L.total) {
+      cx->valid = 0;
+      return;
+    }
+    const int r = it % L.nrt;
+    int rest = it / L.nrt;
+    const int kzt = rest % L.nkz;
+    rest /= L.nkz;
+    const int fld = rest % L.nfld, ml = L.mlo + rest / L.nfld;
+    const int mglob = a.m0 + ml;
+    const int nn = ws_nn_of_m(mglob, a.nrc, a.npc);
+    if (r * WSF_MT >= nn) continue;      // nothing retained in this row tile: the zero-fill pass covers it
+    cx->kz0 = kzt * WSF_NTC;
+    cx->in = a.fb.in[fld] + (size_t)ml * a.nrl + (size_t)cx->kz0 * a.nrl * a.npl;
+    cx->out = a.fb.out[fld] + (size_t)ml * a.nrl;
+    cx->lnval = (mglob == 0) ? a.fb.ln[fld] : 0.0;
+    cx->nn = nn;
+    cx->n0 = r * WSF_MT;
+    cx->mglob = mglob;
+    cx->valid = 1;
     return;
   }
-  int r = 0;
-  while (it >= L.start[r + 1]) ++r;
-  const int idx = it - L.start[r];
-  const int kzt = idx % L.nkz, rest = idx / L.nkz;
-  const int fld = rest % L.nfld, ml = L.mlo + rest / L.nfld;
-  const int mglob = a.m0 + ml;
-  cx->kz0 = kzt * WSF_NTC;
-  cx->in = a.fb.in[fld] + (size_t)ml * a.nrl + (size_t)cx->kz0 * a.nrl * a.npl;
-  cx->out = a.fb.out[fld] + (size_t)ml * a.nrl;
-  cx->lnval = (mglob == 0) ? a.fb.ln[fld] : 0.0;
-  cx->nn = ws_nn_of_m(mglob, a.nrc, a.npc);
-  cx->n0 = r * WSF_MT;
-  cx->mglob = mglob;
-  cx->valid = 1;
 }
 
 // 3-D TMA box load: table(i, n, m) -> swizzled shared box
@@ -623,9 +644,11 @@ static int ws_setup() {
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&g_ws_sms, cudaDevAttrMultiProcessorCount, dev));
   CUDA_TRY(cudaMalloc((void **)&g_ws_ctr, 4 * sizeof(unsigned int)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(BwdSmemWS)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(BwdSmemWS)));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(BwdSmemWS)));
   CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(FwdSmemWS)));
@@ -681,6 +704,8 @@ void leg_ws_reset() { g_tmaps.clear(); }
 // the bulk copies need 16-byte aligned table rows: nr a multiple of 4
 bool leg_ws_supported(const LegArgs &a) { return (a.nrh & 1) == 0; }
 
+int launch_slab_ship(const PeerTable &t, const FieldBatch &fb, cudaStream_t st);   // dist.cu
+
 // `a` has its batch filled in (legendre.cu: with_batch)
 int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   MLEGS_TRY(ws_setup());
@@ -699,16 +724,26 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   L.ctr = g_ws_ctr;
   CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
   const int grid = std::max(1, std::min(g_ws_sms, std::max(L.total, 1)));
-  prof_begin(a.peer ? "legendre_backward_put" : "legendre_backward", st);
-  if (a.peer) {
-    leg_backward_ws_kernel<true><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
+  // several ranks: with an output buffer per scalar the rows are staged locally in destination order and shipped as
+  // long runs (launch_slab_ship); without one they are put straight into the peers' windows
+  // (2 ranks, 128^3 per rank: direct puts 192 us, staged 120 + 133 us; 8 ranks: the direct puts are 256-byte runs of
+  // 128-byte stores and reach 243 GB/s).  Staged when a peer's share of the rows is shorter than 48 (768-byte runs).
+  static const char *force = getenv("MLEGS_EXCHANGE12");   // "stage" / "put": A/B timing
+  bool stage = a.peer && a.fb.out[0] != nullptr && (a.nrdim / a.peer->nranks) < 48;
+  if (a.peer && a.fb.out[0] != nullptr && force) stage = force[0] == 's';
+  prof_begin(a.peer ? (stage ? "legendre_backward_stage" : "legendre_backward_put") : "legendre_backward", st);
+  if (stage) {
+    leg_backward_ws_kernel<2><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
+  } else if (a.peer) {
+    leg_backward_ws_kernel<1><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
   } else {
     PeerTable none;
     memset(&none, 0, sizeof(none));
-    leg_backward_ws_kernel<false><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, none);
+    leg_backward_ws_kernel<0><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, none);
   }
   prof_end(st);
   KERNEL_CHECK();
+  if (stage) MLEGS_TRY(launch_slab_ship(*a.peer, a.fb, st));
   return MLEGS_OK;
 }
 
@@ -726,8 +761,8 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   const double *tab = a.w ? c.d_pfw : a.pf;
   const CUtensorMap *tm = nullptr;
   MLEGS_TRY(table_tmap(tab, a.nrh, a.ne, c.p.npchop, &tm));
-  // tiles: for every row tile r, the local columns whose truncation reaches into it (nn(m) is non-increasing in m,
-  // so they form a prefix) x scalars x z tiles, numbered heaviest first
+  // tiles: (column with nn(m) > 0) x scalar x z tile x row tile of the widest column; nn(m) is non-increasing in m,
+  // so the columns with work form a prefix
   LegItemsF L;
   L.nkz = (a.nzl + WSF_NTC - 1) / WSF_NTC;
   L.nfld = a.fb.n;
@@ -737,16 +772,10 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
     const int m = a.m0 + ml;
     return m < a.npc ? std::min(std::max(std::min(a.nrc, a.nrc - m), 0), a.nrdim) : 0;
   };
-  if (L.mlo < a.npl && nn_host(L.mlo) > WS_MAXRT * WSF_MT)
-    return fail(MLEGS_E_ARG, "rtrans_forward: more than 2048 radial modes are not supported");
-  int total = 0;
-  L.start[0] = 0;
-  for (int r = 0; r < WS_MAXRT; ++r) {
-    int cnt = 0;
-    for (int ml = L.mlo; ml < a.npl && nn_host(ml) > r * WSF_MT; ++ml) ++cnt;
-    total += cnt * L.nfld * L.nkz;
-    L.start[r + 1] = total;
-  }
+  int mcount = 0;
+  for (int ml = L.mlo; ml < a.npl && nn_host(ml) > 0; ++ml) ++mcount;
+  L.nrt = mcount > 0 ? (nn_host(L.mlo) + WSF_MT - 1) / WSF_MT : 1;
+  const int total = mcount * L.nfld * L.nkz * L.nrt;
   L.total = total;
   CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
   const int grid = std::max(1, std::min(g_ws_sms, std::max(total, 1)));

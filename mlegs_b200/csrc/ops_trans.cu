@@ -208,7 +208,7 @@ int trans_impl(mlegs_field *s, const char *to) {
           PeerTable pt;
           void *landed = nullptr;
           MLEGS_TRY(dist_begin_put(&pt, &landed));
-          MLEGS_TRY(stage_r(s, false, at, nullptr, &pt));
+          MLEGS_TRY(stage_r(s, false, at, other(at), &pt));   // other(at): staging buffer of the (1,2) exchange
           field_set_layout(s, true);
           at = (cplx *)landed;
           exchanged = true;
@@ -350,7 +350,7 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
           PeerTable pt;
           void *landed = nullptr;
           MLEGS_TRY(dist_begin_put(&pt, &landed));
-          make(true, &fb);
+          make(false, &fb);   // the other buffer of every scalar stages its rows in destination order
           MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, &pt, &fb));
           landed_in_window(landed, true);
         } else {

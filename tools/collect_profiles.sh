@@ -3,11 +3,15 @@
 # Output goes to gpurun_out/; tools/ncu_summary.py turns the reports into the CSVs kept under profiles/.
 set -x
 mkdir -p gpurun_out
-TAG=${1:-r1b}
+TAG=${1:-r1}
 # every launch of a short bench run with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches128_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --fields 16 --no-cpu > gpurun_out/launches128_$TAG.log 2>&1
-# one batched round trip at 128^3 (8 scalars per launch): all six kernels, full sets (skip the first round trip)
+# one batched round trip at 128^3 (8 scalars per launch, the bench's launch shape): all six kernels, full sets
+# (skip the first round trip)
 ncu --set full --clock-control none --import-source on -k regex:'fft_reg|leg_' -s 6 -c 6 -o gpurun_out/trans128_full_$TAG \
     python tools/prof_roundtrip.py --size 128 --reps 3 --batch 8 > gpurun_out/ncu128_$TAG.log 2>&1
+# the north-star size, one scalar per launch
+ncu --set full --clock-control none --import-source on -k regex:'fft_reg|leg_' -s 6 -c 6 -o gpurun_out/trans512_full_$TAG \
+    python tools/prof_roundtrip.py --size 512 --reps 2 > gpurun_out/ncu512_$TAG.log 2>&1
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/clocks_after.csv
