@@ -223,6 +223,12 @@ int mlegs_b200_dist_detach(void);
  * The device put kernel runs the same addressing code (dist:395-504's subarray datatypes). */
 int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim, int nz, int *dst_rank,
                             long long *dst_index);
+/* Host-only plan of the STAGED exchange(1,2) (no CUDA needed): for every element of rank `rank`'s local
+ * (nrdim, m_cnt, nz) block in memory order, its index inside the local staging buffer the Legendre synthesis writes
+ * (stage_index), and -- for every staging index -- the rank and linear index the ship kernel moves it to
+ * (ship_rank, ship_index; both of length nrdim*m_cnt*nz).  Composing the two must equal dist_put_map(dir = 1). */
+int mlegs_b200_dist_stage_map(int rank, int nranks, int nrdim, int npdim, int nz, long long *stage_index,
+                              int *ship_rank, long long *ship_index);
 /* Sum n HOST doubles over all ranks on the library's own peer windows (the app-level MPI_Allreduce of
  * check_stability, apps/vortical_flow_3d.f90:404); identical result on every rank; no-op on one rank. */
 int mlegs_b200_dist_allreduce(double *host_inout, int n);

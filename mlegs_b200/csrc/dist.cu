@@ -320,6 +320,37 @@ int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim,
   return MLEGS_OK;
 }
 
+/* Host-only: the staged exchange(1,2) of rank `rank` as two maps, produced by the very addressing code the device runs:
+ * stage_index = slab_stage_index (Legendre synthesis epilogue, MODE 2), ship_* = the run arithmetic of slab_ship_kernel. */
+int mlegs_b200_dist_stage_map(int rank, int nranks, int nrdim, int npdim, int nz, long long *stage_index,
+                              int *ship_rank, long long *ship_index) {
+  if (nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks)
+    return fail(MLEGS_E_COMM, "mlegs_b200_dist_stage_map: bad arguments");
+  int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
+  for (int q = 0; q < nranks; ++q) {
+    decompose(nrdim, nranks, q, &r_cnt[q], &r_off[q]);
+    decompose(npdim, nranks, q, &m_cnt[q], &m_off[q]);
+  }
+  const int mc = m_cnt[rank];
+  size_t idx = 0;
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < mc; ++j)
+      for (int i = 0; i < nrdim; ++i, ++idx)
+        stage_index[idx] = (long long)slab_stage_index(rank, nranks, r_cnt, r_off, m_cnt, nz, i, j, k);
+  // the ship kernel: per (peer q, plane k) one run of mc * r_cnt[q] elements
+  for (int q = 0; q < nranks; ++q)
+    for (int k = 0; k < nz; ++k) {
+      const int len = mc * r_cnt[q];
+      const size_t s0 = (size_t)r_off[q] * mc * nz + (size_t)k * len;
+      const size_t d0 = ((size_t)k * npdim + m_off[rank]) * r_cnt[q];
+      for (int e = 0; e < len; ++e) {
+        ship_rank[s0 + e] = q;
+        ship_index[s0 + e] = (long long)(d0 + e);
+      }
+    }
+  return MLEGS_OK;
+}
+
 /* sum `n` HOST doubles over all ranks (the app-level MPI_Allreduce of e.g. check_stability,
  * apps/vortical_flow_3d.f90:404, expressed on the library's own peer windows) */
 int mlegs_b200_dist_allreduce(double *host_inout, int n) {

@@ -60,3 +60,17 @@ def put_map(direction: int, rank: int, nranks: int, nrdim: int, npdim: int, nz: 
                                              dst_rank.ctypes.data_as(C.c_void_p),
                                              dst_index.ctypes.data_as(C.c_void_p)))
     return dst_rank, dst_index
+
+
+def stage_map(rank: int, nranks: int, nrdim: int, npdim: int, nz: int):
+    """Host-only plan of the staged exchange(1,2) of one rank (no CUDA): stage_index per local element, and
+    (ship_rank, ship_index) per staging index."""
+    n = nrdim * decompose(npdim, nranks, rank)[0] * nz
+    stage_index = np.zeros(n, dtype=np.int64)
+    ship_rank = np.full(n, -1, dtype=np.int32)
+    ship_index = np.full(n, -1, dtype=np.int64)
+    check(_lib.lib().mlegs_b200_dist_stage_map(rank, nranks, nrdim, npdim, nz,
+                                               stage_index.ctypes.data_as(C.c_void_p),
+                                               ship_rank.ctypes.data_as(C.c_void_p),
+                                               ship_index.ctypes.data_as(C.c_void_p)))
+    return stage_index, ship_rank, ship_index

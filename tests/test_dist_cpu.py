@@ -92,3 +92,21 @@ def test_decompose_covers_the_axis():
             assert segs[0][1] == 0 and sum(c for c, _ in segs) == n
             for (c0, o0), (c1, o1) in zip(segs, segs[1:]):
                 assert o1 == o0 + c0 and c0 >= c1    # first mod(n,p) ranks get one extra (mlegs_envir_mpi.f90:20-28)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_staged_exchange_equals_direct_put(world):
+    """The staged exchange(1,2) (Legendre epilogue -> local staging buffer in destination order -> ship kernel's
+    contiguous runs) must deliver every element exactly where the direct put does; the staging map is a
+    permutation of the local block and every ship run is contiguous on both sides."""
+    from mlegs_b200 import dist as mdist
+    nrdim, npdim, nz = 35, 9, 4
+    for rank in range(world):
+        dst_rank, dst_index = mdist.put_map(1, rank, world, nrdim, npdim, nz)
+        stage, ship_rank, ship_index = mdist.stage_map(rank, world, nrdim, npdim, nz)
+        n = stage.size
+        assert n == dst_rank.size
+        assert np.array_equal(np.sort(stage), np.arange(n)), "staging map is not a permutation"
+        assert (ship_rank >= 0).all() and (ship_index >= 0).all(), "ship runs do not cover the staging buffer"
+        assert np.array_equal(ship_rank[stage], dst_rank)
+        assert np.array_equal(ship_index[stage], dst_index)
