@@ -256,8 +256,10 @@ int setup_fft_kernels() {
 
 int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, long long batch0,
                      long long stride_pt, int batch1, long long stride_b1, const double *tw, int tw_order,
-                     double scale, cudaStream_t st, const FieldBatch *fb) {
+                     double scale, cudaStream_t st, const FieldBatch *fb, const RowScale *rs) {
   if (batch0 <= 0 || batch1 <= 0) return MLEGS_OK;
+  if (rs && rs->mode != 0 && !fft_reg_supported(plan.n))
+    return fail(MLEGS_E_STATE, "fft: fused row scaling needs the register kernels");
   static const char *names[4] = {"fft_z_forward", "fft_z_backward", "fft_phi_forward", "fft_phi_backward"};
   if (fb && fb->n > 0 && !fft_reg_supported(plan.n)) {
     // lengths outside the register kernels: one launch per scalar
@@ -269,7 +271,7 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
   if (fft_reg_supported(plan.n)) {
     prof_begin(names[(int)mode], st);
     int rc = launch_fft_reg(mode, plan.n, in, out, batch0 * batch1, batch0, stride_b1, stride_pt, tw, tw_order, scale,
-                            nullptr, 0, 0, st, nullptr, 0, fb);
+                            nullptr, 0, 0, st, nullptr, 0, fb, rs);
     prof_end(st);
     MLEGS_TRY(rc);
     KERNEL_CHECK();
@@ -306,11 +308,11 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
 
 int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
                                const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
-                               cudaStream_t st, const FieldBatch *fb) {
+                               cudaStream_t st, const FieldBatch *fb, const RowScale *rs) {
   if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: the fused exchange needs the register kernels");
   prof_begin("fft_phi_forward_put", st);
   int rc = launch_fft_reg(FFT_R2C_FWD, plan.n, in, nullptr, rows * nz, rows, plane, rows, tw, tw_order, scale, nullptr, 0, 0,
-                          st, &peer, nrdim, fb);
+                          st, &peer, nrdim, fb, rs);
   prof_end(st);
   MLEGS_TRY(rc);
   KERNEL_CHECK();

@@ -171,8 +171,18 @@ struct FftRegArgs {
   // that owns m, at row r_off[me] + i of its (nrdim, m_cnt, nz) block; the kernel ends with the exchange barrier
   int use_peer;
   int nrdim;
+  RowScale rs;           // fused r*u (r2c loads) / u/r (c2r stores) of the scalars in rs.mask
   PeerTable pt;
 };
+
+// x / b with the reciprocal y = RN(1/b) computed once per line: q = RN(x y), r = x - b q (exact in an fma),
+// q' = RN(q + r y) is the correctly rounded quotient (Markstein), i.e. what `x / b` returns, at 3 instead of ~10 FP64
+// instructions per value.
+__device__ __forceinline__ double div_by(double x, double b, double y) {
+  const double q = x * y;
+  const double r = fma(-b, q, x);
+  return fma(r, y, q);
+}
 
 // MODE: FFT_C2C_FWD / FFT_C2C_BWD / FFT_R2C_FWD / FFT_C2R_BWD (kernels.h).
 // one tile = L lines of one scalar (blockIdx.y); `blk` = tile index
@@ -201,6 +211,17 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
   }
   const cplx *gin = a.in[blockIdx.y] + base;
   cplx *gout = a.out[blockIdx.y] + base;
+  // fused row scaling (real modes only: lines are (row, plane) pairs, row = q mod batch0)
+  double rv = 1.0, rinv = 1.0;
+  bool scaled = false;
+  if ((MODE == FFT_R2C_FWD || MODE == FFT_C2R_BWD) && a.rs.mode != 0 && ((a.rs.mask >> blockIdx.y) & 1u) && ok) {
+    const int ig = a.rs.r0 + (int)(q % a.batch0);
+    if (ig < a.rs.nr) {
+      rv = __ldg(&a.rs.r[ig]);
+      if (MODE == FFT_C2R_BWD) rinv = 1.0 / rv;
+      scaled = true;
+    }
+  }
   const int tw_unit = a.tw_order / N;   // 1 for c2c; 2 for the real modes (tw_order == 2N)
   const cplx zero = make_double2(0.0, 0.0);
 
@@ -236,6 +257,7 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
 #pragma unroll
     for (int j = 0; j < E; ++j) {
       cplx x = ok ? gin[(long long)(t + T * j) * a.stride_pt] : zero;
+      if (MODE == FFT_R2C_FWD && scaled) x = make_double2(x.x * rv, x.y * rv);
       v[j] = (MODE == FFT_C2C_BWD) ? cconj(x) : x;
     }
   }
@@ -303,12 +325,20 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
       cplx x = v[qq + u * QL];
       if (MODE == FFT_C2C_BWD || MODE == FFT_C2R_BWD) x = cconj(x);
       const int idx = out_index<N, E, RL, NSL>(t, qq, u);
-      if (ok) gout[(long long)idx * a.stride_pt] = make_double2(x.x * a.scale, x.y * a.scale);
+      if (ok) {
+        cplx val = make_double2(x.x * a.scale, x.y * a.scale);
+        if (MODE == FFT_C2R_BWD && scaled) val = make_double2(div_by(val.x, rv, rinv), div_by(val.y, rv, rinv));
+        gout[(long long)idx * a.stride_pt] = val;
+      }
     }
   if (MODE == FFT_C2R_BWD) {
-    // padding column keeps the Nyquist input times np (quirk Q3; ops:1702-1705)
+    // padding column keeps the Nyquist input times np (quirk Q3; ops:1702-1705); a separate rscale pass would divide it too
     const double fac = (double)(2 * N);
-    if (t == 0 && ok) gout[(long long)N * a.stride_pt] = make_double2(nyq.x * fac, nyq.y * fac);
+    if (t == 0 && ok) {
+      cplx val = make_double2(nyq.x * fac, nyq.y * fac);
+      if (scaled) val = make_double2(div_by(val.x, rv, rinv), div_by(val.y, rv, rinv));
+      gout[(long long)N * a.stride_pt] = val;
+    }
   }
 }
 
@@ -381,8 +411,9 @@ bool fft_reg_supported(int n) { return n == 32 || n == 64 || n == 128 || n == 25
 int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
                    long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
                    const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer, int nrdim,
-                   const FieldBatch *fb) {
+                   const FieldBatch *fb, const RowScale *rs) {
   FftRegArgs a;
+  if (rs) a.rs = *rs;
   int nfields = 1;
   if (fb && fb->n > 0) {
     nfields = fb->n;

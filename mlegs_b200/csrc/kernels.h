@@ -18,6 +18,17 @@ struct FieldBatch {
   double ln[MLEGS_MAXB];
 };
 
+// Row scaling fused into the azimuthal FFT of some scalars of a batch: rows r0 + i < nr are multiplied by r(i) as they
+// are loaded (mode 1: the r*u of vec2tp, ops:1337-1355, on the r2c side) or divided by r(i) as they are stored
+// (mode 2: the u/r of tp2vec, ops:1509-1527, on the c2r side).  Same operations in the same order as a separate
+// rscale pass, so results are bit-identical.
+struct RowScale {
+  const double *r = nullptr;
+  int mode = 0;
+  unsigned mask = 0;     // bit i: scalar i of the batch is scaled
+  int r0 = 0, nr = 0;
+};
+
 // prof.cu: optional CUDA-event timing around each launch
 void prof_begin(const char *name, cudaStream_t st);
 void prof_end(cudaStream_t st);
@@ -30,7 +41,7 @@ int setup_fft_kernels();
 enum FftMode { FFT_C2C_FWD = 0, FFT_C2C_BWD = 1, FFT_R2C_FWD = 2, FFT_C2R_BWD = 3 };
 int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, long long batch0,
                      long long stride_pt, int batch1, long long stride_b1, const double *tw, int tw_order,
-                     double scale, cudaStream_t st, const FieldBatch *fb = nullptr);
+                     double scale, cudaStream_t st, const FieldBatch *fb = nullptr, const RowScale *rs = nullptr);
 
 // fft_reg.cu: register-resident fast path for power-of-two lengths 32..1024
 bool fft_reg_supported(int n);
@@ -38,11 +49,11 @@ struct PeerTable;   // dist_dev.cuh
 int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nlines, long long batch0,
                    long long stride_b1, long long stride_pt, const double *tw, int tw_order, double scale,
                    const int *colstart, int ncols, int nrl, cudaStream_t st, const PeerTable *peer = nullptr,
-                   int nrdim = 0, const FieldBatch *fb = nullptr);
+                   int nrdim = 0, const FieldBatch *fb = nullptr, const RowScale *rs = nullptr);
 // azimuthal r2c FFT whose stores are the exchange(2,1) puts (several ranks, register kernels only)
 int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long rows, int nz, long long plane,
                                const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
-                               cudaStream_t st, const FieldBatch *fb = nullptr);
+                               cudaStream_t st, const FieldBatch *fb = nullptr, const RowScale *rs = nullptr);
 // axial FFT of the retained lines only (rows < nn(m) of each local column); colstart = device prefix sums
 int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx *out, const int *colstart, int ncols,
                          int nrl, long long nlines, long long stride_pt, const double *tw, int tw_order, double scale,

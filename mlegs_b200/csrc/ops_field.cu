@@ -684,6 +684,15 @@ int vecprod_impl(mlegs_field *vr, mlegs_field *vp, mlegs_field *vz, const mlegs_
                         c.p.np / 2, c.p.nz, strm());
 }
 
+int trans_many_scaled(int n, mlegs_field *const *s, const char *to, unsigned rs_mask, const void *const *src);   // ops_trans.cu
+
+// rows i < nr of a PPP scalar times r(i) (divide = 0) or over r(i) (divide = 1)
+int launch_rscale_field(mlegs_field *f, int divide) {
+  Context &c = ctx();
+  const size_t ncols = (size_t)f->loc_sz[1] * f->loc_sz[2];
+  return launch_rscale((cplx *)f->e, f->loc_sz[0], ncols, f->loc_st[0], c.p.nr, c.d_r, divide, strm());
+}
+
 int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr, mlegs_field *vp, mlegs_field *vz) {
   MLEGS_TRY(ready());
   Context &c = ctx();
@@ -727,12 +736,9 @@ int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr,
   uz->nrchop_offset = 0;
   MLEGS_TRY(chop_impl(uz));
   // the three backward transforms (ops:1503-1505, 1541) are independent: one launch per stage for all of them
+  // ur/r and up/r (ops:1509-1527) ride on the stores of the backward azimuthal FFT
   mlegs_field *comps[3] = {ur, up, uz};
-  MLEGS_TRY(trans_many_impl(3, comps, "PPP"));
-  size_t ncols = (size_t)ur->loc_sz[1] * ur->loc_sz[2];
-  MLEGS_TRY(launch_rscale((cplx *)ur->e, ur->loc_sz[0], ncols, ur->loc_st[0], c.p.nr, c.d_r, 1, strm()));
-  MLEGS_TRY(launch_rscale((cplx *)up->e, up->loc_sz[0], ncols, up->loc_st[0], c.p.nr, c.d_r, 1, strm()));
-  return MLEGS_OK;
+  return trans_many_scaled(3, comps, "PPP", 0x3u, nullptr);
 }
 
 int tp2curlvec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *wr, mlegs_field *wp, mlegs_field *wz) {
@@ -760,17 +766,22 @@ int vec2tp_impl(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field 
   psi->ln = 0.0;
   chi->ln = 0.0;
   mlegs_field ur = temp_like(vr, 1), up = temp_like(vp, 2), uz = temp_like(vz, 3);
-  MLEGS_TRY(copy_data(&ur, vr));
-  MLEGS_TRY(copy_data(&up, vp));
-  MLEGS_TRY(copy_data(&uz, vz));
-  size_t ncols = (size_t)ur.loc_sz[1] * ur.loc_sz[2];
-  MLEGS_TRY(launch_rscale((cplx *)ur.e, ur.loc_sz[0], ncols, ur.loc_st[0], c.p.nr, c.d_r, 0, strm()));   // r*ur
-  MLEGS_TRY(launch_rscale((cplx *)up.e, up.loc_sz[0], ncols, up.loc_st[0], c.p.nr, c.d_r, 0, strm()));   // r*up
+  {   // metadata of the inputs; the data is read straight from vr, vp, vz by the first transform stage
+    void *e1 = ur.e, *e2 = up.e, *e3 = uz.e;
+    ur = *vr;
+    up = *vp;
+    uz = *vz;
+    ur.e = e1;
+    up.e = e2;
+    uz.e = e3;
+  }
 
   // ur, uz -> 'PFF' (phi and z spectral, r physical), ops:1357-1363, 1375-1381
-  {   // the three azimuthal FFTs in one launch, then the axial FFTs of ur and uz in one launch
+  {   // the three azimuthal FFTs in one launch (r*ur, r*up of ops:1337-1355 fused into its loads, no copies of the
+      // inputs), then the axial FFTs of ur and uz in one launch
     mlegs_field *comps[3] = {&ur, &up, &uz};
-    MLEGS_TRY(trans_many_impl(3, comps, "PFP"));
+    const void *srcs[3] = {vr->e, vp->e, vz->e};
+    MLEGS_TRY(trans_many_scaled(3, comps, "PFP", 0x3u, srcs));
     if (has_z) {
       FieldBatch fb;
       fb.n = 2;

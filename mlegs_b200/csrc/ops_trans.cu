@@ -61,13 +61,14 @@ static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
 
 // One stage, reading `src` and writing `dst` (may be equal for the FFT stages).  fb != nullptr: the stage runs on
 // the fb->n scalars of the batch in one launch (all with the layout/metadata of `s`; src/dst are ignored).
-int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb = nullptr);
-int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb) {
+int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb = nullptr,
+              const RowScale *rs = nullptr);
+int stage_phi(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb, const RowScale *rs) {
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   long long rows = s->loc_sz[0];
   return launch_fft_lines(forward ? FFT_R2C_FWD : FFT_C2R_BWD, c.plan_p, src, dst, rows, rows, s->loc_sz[2],
-                          rows * (long long)s->loc_sz[1], c.d_tw_p, c.p.np, forward ? 1.0 / c.p.np : 1.0, st, fb);
+                          rows * (long long)s->loc_sz[1], c.d_tw_p, c.p.np, forward ? 1.0 / c.p.np : 1.0, st, fb, rs);
 }
 
 int stage_z(const mlegs_field *s, bool forward, const cplx *src, cplx *dst, const FieldBatch *fb = nullptr);
@@ -267,7 +268,16 @@ size_t dist_field_stride();
 // One group of at most MLEGS_MAXB scalars (several ranks: at most dist_window_batch()).  Every scalar has a current
 // location (its own buffer, its batch scratch buffer, or -- right after a fused exchange -- its slab of this rank's
 // receive window); stages go out of place whenever that lets the last one land at home.
-static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
+// Options of a batched transform used by the vector operations: scalars whose rows are multiplied by r on the way
+// into the forward azimuthal FFT / divided by r on the way out of the backward one (bit i of rs_mask), and scalars
+// whose input is read from another (read-only) buffer than their own (src[i] != nullptr: the first stage then goes out
+// of place, which replaces a field copy).
+struct TransOpts {
+  unsigned rs_mask = 0;
+  const void *src[MLEGS_MAXB] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+static int trans_group(int n, mlegs_field *const *s, int cur, int dst, const TransOpts *opt = nullptr, int i0 = 0) {
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   const bool has_p = c.p.np > 1, has_z = c.p.nz > 1;
@@ -275,7 +285,17 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
   const bool compact_ok = has_z && fft_reg_supported(c.plan_z.n);
   cplx *home[MLEGS_MAXB], *tmp[MLEGS_MAXB], *at[MLEGS_MAXB];
   MLEGS_TRY(batch_scratch(n, tmp));
-  for (int i = 0; i < n; ++i) at[i] = home[i] = (cplx *)s[i]->e;
+  for (int i = 0; i < n; ++i) {
+    home[i] = (cplx *)s[i]->e;
+    at[i] = (opt && opt->src[i0 + i]) ? (cplx *)const_cast<void *>(opt->src[i0 + i]) : home[i];   // never written to
+  }
+  const bool foreign_src = at[0] != home[0];
+  RowScale rs;
+  if (opt && ((opt->rs_mask >> i0) & ((1u << n) - 1u))) {
+    rs.r = c.d_r;
+    rs.mask = (opt->rs_mask >> i0) & ((1u << n) - 1u);
+    rs.nr = c.p.nr;
+  }
   bool rows_zero = false;
   const mlegs_field *s0 = s[0];
   auto other = [&](int i) { return at[i] == home[i] ? tmp[i] : home[i]; };
@@ -309,13 +329,17 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
           MLEGS_TRY(dist_begin_put(&pt, &landed));
           make(true, &fb);
           const long long rows = s0->loc_sz[0];
+          rs.mode = rs.mask ? 1 : 0;
+          rs.r0 = s0->loc_st[0];
           MLEGS_TRY(launch_fft_phi_forward_put(c.plan_p, nullptr, rows, s0->loc_sz[2], rows * (long long)s0->loc_sz[1],
-                                               c.d_tw_p, c.p.np, 1.0 / c.p.np, pt, c.nrdim, st, &fb));
+                                               c.d_tw_p, c.p.np, 1.0 / c.p.np, pt, c.nrdim, st, &fb, &rs));
           landed_in_window(landed, false);
         } else {
-          const bool inplace = !(dst >= 2);
+          const bool inplace = !(dst >= 2) && !foreign_src;
           make(inplace, &fb);
-          MLEGS_TRY(stage_phi(s0, true, nullptr, nullptr, &fb));
+          rs.mode = rs.mask ? 1 : 0;
+          rs.r0 = s0->loc_st[0];
+          MLEGS_TRY(stage_phi(s0, true, nullptr, nullptr, &fb, &rs));
           moved(fb);
         }
       } else if (cur == 1) {
@@ -363,7 +387,9 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
         make(inplace, &fb);
         if (!inplace)
           for (int i = 0; i < n; ++i) fb.out[i] = home[i];
-        MLEGS_TRY(stage_phi(s[0], false, nullptr, nullptr, &fb));
+        rs.mode = rs.mask ? 2 : 0;
+        rs.r0 = s[0]->loc_st[0];
+        MLEGS_TRY(stage_phi(s[0], false, nullptr, nullptr, &fb, &rs));
         moved(fb);
       }
       --cur;
@@ -379,7 +405,43 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst) {
   return MLEGS_OK;
 }
 
-int trans_many_impl(int n, mlegs_field *const *s, const char *to) {
+static int trans_many_opt(int n, mlegs_field *const *s, const char *to, const TransOpts *opt);
+int trans_many_impl(int n, mlegs_field *const *s, const char *to) { return trans_many_opt(n, s, to, nullptr); }
+
+int launch_rscale_field(mlegs_field *f, int divide);   // ops_field.cu
+
+// The vector operations' entry: scalars in PPP (forward, r*u fused into the loads, inputs read from src[]) or on
+// their way to PPP (backward, u/r fused into the stores).  When the batched register-FFT path cannot be taken the
+// same thing is done with explicit copies and rscale passes around the plain transforms.
+int trans_many_scaled(int n, mlegs_field *const *s, const char *to, unsigned rs_mask, const void *const *src) {
+  Context &c = ctx();
+  TransOpts o;
+  o.rs_mask = rs_mask;
+  if (n > MLEGS_MAXB) return fail(MLEGS_E_ARG, "trans_many: too many scalars");
+  for (int i = 0; i < n && src; ++i) o.src[i] = src[i];
+  const int cur = n > 0 ? space_id(s[0]->space) : -1, dst = space_id(to);
+  const bool forward = cur == 0 && dst >= 1, backward = dst == 0 && cur >= 1;
+  bool fused = n >= 2 && c.p.np > 1 && fft_reg_supported(c.plan_p.n) && (forward || backward);
+  if (fused && c.nranks > 1) fused = (c.nrh % 2 == 0) && !(dst == 0 && cur == 1) && dist_window_batch() >= n;
+  for (int i = 1; i < n && fused; ++i)
+    fused = space_id(s[i]->space) == cur && s[i]->nrchop_offset == s[0]->nrchop_offset &&
+            s[i]->npchop_offset == s[0]->npchop_offset && s[i]->nzchop_offset == s[0]->nzchop_offset;
+  if (fused) return trans_many_opt(n, s, to, &o);
+  // explicit form
+  for (int i = 0; i < n; ++i) {
+    if (o.src[i] && o.src[i] != s[i]->e) {
+      size_t ne = (size_t)s[i]->loc_sz[0] * s[i]->loc_sz[1] * s[i]->loc_sz[2];
+      CUDA_TRY(cudaMemcpyAsync(s[i]->e, o.src[i], ne * sizeof(cplx), cudaMemcpyDeviceToDevice, (cudaStream_t)c.stream));
+    }
+    if (forward && ((rs_mask >> i) & 1u)) MLEGS_TRY(launch_rscale_field(s[i], 0));
+  }
+  MLEGS_TRY(trans_many_opt(n, s, to, nullptr));
+  for (int i = 0; i < n; ++i)
+    if (backward && ((rs_mask >> i) & 1u)) MLEGS_TRY(launch_rscale_field(s[i], 1));
+  return MLEGS_OK;
+}
+
+static int trans_many_opt(int n, mlegs_field *const *s, const char *to, const TransOpts *opt) {
   Context &c = ctx();
   if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
   if (n <= 0) return MLEGS_OK;
@@ -397,6 +459,7 @@ int trans_many_impl(int n, mlegs_field *const *s, const char *to) {
   }
   // mixed states: nothing to share
   if (n == 1 || !uniform) {
+    if (opt) return fail(MLEGS_E_STATE, "trans_many: fused options need scalars of one state");
     for (int i = 0; i < n; ++i) MLEGS_TRY(trans_impl(s[i], to));
     return MLEGS_OK;
   }
@@ -410,6 +473,7 @@ int trans_many_impl(int n, mlegs_field *const *s, const char *to) {
     const bool fused_ok = fft_reg_supported(c.plan_p.n) && (c.nrh % 2 == 0) && !(dst == 0 && cur == 1);
     group = std::min(group, dist_window_batch());
     if (crosses && (!fused_ok || group < 2)) {
+      if (opt) return fail(MLEGS_E_STATE, "trans_many: fused options need the fused exchange");
       for (int i = 0; i < n; ++i) MLEGS_TRY(trans_impl(s[i], to));
       return MLEGS_OK;
     }
@@ -418,7 +482,7 @@ int trans_many_impl(int n, mlegs_field *const *s, const char *to) {
     LegArgs a;
     MLEGS_TRY(rtrans_args(s[0], cur < dst ? "rtrans_forward" : "rtrans_backward", &a));
   }
-  for (int i0 = 0; i0 < n; i0 += group) MLEGS_TRY(trans_group(std::min(group, n - i0), s + i0, cur, dst));
+  for (int i0 = 0; i0 < n; i0 += group) MLEGS_TRY(trans_group(std::min(group, n - i0), s + i0, cur, dst, opt, i0));
   return MLEGS_OK;
 }
 
