@@ -1,5 +1,8 @@
 // Radial mapped-Legendre transform as batched FP64 tensor-core GEMMs (DMMA m8n8k4), one GEMM
-// problem per azimuthal wavenumber m.  Replaces rtrans_forward / rtrans_backward of
+// problem per azimuthal wavenumber m.  These are the cp.async kernels of the first half of round 1; the production
+// path is the warp-specialised TMA-fed pair in legendre_ws.cu (launch_leg_* below dispatch to it), and the kernels
+// here remain for radial sizes whose table rows are not 16-byte aligned (nr not a multiple of 4) and for A/B timing
+// (MLEGS_LEG_NO_WS=1).  Replaces rtrans_forward / rtrans_backward of
 // /root/reference/src/submodules/mlegs_scalar_ops.f90:1852-2008, which promote the real table to
 // complex and call zgemm once per m on strided slices.
 //

@@ -15,6 +15,10 @@ CASES = {
     "gate3d": (32, 16, 8, 32, 9, 5, 4.0, 8),           # tools/validate_tutorials.py:222-238
     "radix35": (36, 30, 20, 30, 12, 9, 2.0, 4),        # np, nz with factors 3 and 5; chops below the maximum
     "cube64": (64, 64, 64, 64, 33, 33, 4.0, 0),
+    # nr/2 odd: table rows are not 16-byte aligned, the cp.async Legendre kernels (legendre.cu) take over
+    "nr30": (30, 16, 8, 30, 9, 5, 2.0, 0),
+    # several row tiles of the TMA-fed Legendre kernels, radial tails in the last stage (nr/2 = 100), 2 n-tiles
+    "nr200": (200, 16, 8, 200, 9, 5, 4.0, 0),
     # every length of the register-resident FFT kernels (fft_reg.cu): np/2 and nz in {32 .. 1024}
     "fft256": (16, 512, 256, 16, 9, 129, 4.0, 0),
     "fftp512": (8, 1024, 32, 8, 5, 17, 4.0, 0),
