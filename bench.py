@@ -35,10 +35,18 @@ UNIT = "GDOF/s"
 NVLINK_PEER_GBPS = 770.0
 
 
+SHAPE = None   # --shape NR,NP,NZ (BASELINE.json configs[4]: the sweep's non-cubic points)
+
+
 def workload(size: int, world: int = 1, weak: str = "nz"):
     """N = 1: the cubic case.  N > 1, weak scaling: the periodic axial direction is extended with the GPU count
     (NZ = size * N, ZLEN scaled alike), so every GPU keeps size^3 degrees of freedom of every field and the same
     Legendre/FFT work per field as the single-GPU run; --weak fields keeps the cube and grows the batch instead."""
+    if SHAPE is not None:
+        nr, npp, nz0 = SHAPE
+        nz = nz0 * world if weak == "nz" else nz0
+        return dict(nr=nr, np=npp, nz=nz, nrchop=nr, npchop=npp // 2 + 1, nzchop=nz // 2 + 1,
+                    ell=4.0, zlen=2.0 * np.pi * max(1, nz // nz0))
     nz = size * world if weak == "nz" else size
     return dict(nr=size, np=size, nz=nz, nrchop=size, npchop=size // 2 + 1, nzchop=nz // 2 + 1,
                 ell=4.0, zlen=2.0 * np.pi * (nz // size))
@@ -417,9 +425,14 @@ def main():
     ap.add_argument("--batch", type=int, default=8,
                     help="scalars per mlegs_b200_trans_many call (1: one mlegs_b200_trans per scalar)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shape", default="", help="NR,NP,NZ of a non-cubic sweep point (overrides --size)")
     ap.add_argument("--weak", default="nz", choices=["nz", "fields"],
                     help="N > 1: grow NZ with N (default, DOF per GPU fixed) or grow the batch of cubic fields")
     args = ap.parse_args()
+    if args.shape:
+        global SHAPE
+        SHAPE = tuple(int(v) for v in args.shape.split(","))
+        assert len(SHAPE) == 3, "--shape NR,NP,NZ"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -186,10 +186,16 @@ __device__ __forceinline__ double div_by(double x, double b, double y) {
 
 // MODE: FFT_C2C_FWD / FFT_C2C_BWD / FFT_R2C_FWD / FFT_C2R_BWD (kernels.h).
 // one tile = L lines of one scalar (blockIdx.y); `blk` = tile index
-template <int MODE, int N, int E, int THREADS>
-__device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long long blk) {
+// EXT: the launch carries a fused exchange and/or fused row scaling (kept out of the plain kernels: the extra state
+// costs them 8-26 registers and a resident CTA per SM)
+template <int MODE, int N, int E, int THREADS, bool EXT>
+__device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk) {
   constexpr int T = N / E, L = THREADS / T;
   using S = Sched<N, E>;
+  // declared here, not passed in: a pointer parameter loses the shared address space (generic loads, 64-bit addresses,
+  // +16 registers on the r2c kernel)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *sm = reinterpret_cast<cplx *>(smem_raw);
   const int tid = threadIdx.x;
   const int l = tid % L, t = tid / L;
   const long long q = blk * L + l;
@@ -214,7 +220,7 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
   // fused row scaling (real modes only: lines are (row, plane) pairs, row = q mod batch0)
   double rv = 1.0, rinv = 1.0;
   bool scaled = false;
-  if ((MODE == FFT_R2C_FWD || MODE == FFT_C2R_BWD) && a.rs.mode != 0 && ((a.rs.mask >> blockIdx.y) & 1u) && ok) {
+  if (EXT && (MODE == FFT_R2C_FWD || MODE == FFT_C2R_BWD) && a.rs.mode != 0 && ((a.rs.mask >> blockIdx.y) & 1u) && ok) {
     const int ig = a.rs.r0 + (int)(q % a.batch0);
     if (ig < a.rs.nr) {
       rv = __ldg(&a.rs.r[ig]);
@@ -257,7 +263,7 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
 #pragma unroll
     for (int j = 0; j < E; ++j) {
       cplx x = ok ? gin[(long long)(t + T * j) * a.stride_pt] : zero;
-      if (MODE == FFT_R2C_FWD && scaled) x = make_double2(x.x * rv, x.y * rv);
+      if (EXT && MODE == FFT_R2C_FWD && scaled) x = make_double2(x.x * rv, x.y * rv);
       v[j] = (MODE == FFT_C2C_BWD) ? cconj(x) : x;
     }
   }
@@ -299,7 +305,7 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
       cplx x = cadd(e, cmul(__ldg(&a.tw[m]), o));
       if (ok) {
         const cplx val = make_double2(x.x * a.scale, x.y * a.scale);
-        if (a.use_peer) {
+        if (EXT && a.use_peer) {
           const long long kk = q / a.batch0;                 // z plane
           const int ii = (int)(q - kk * a.batch0);           // local row
           int dq;
@@ -327,7 +333,7 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
       const int idx = out_index<N, E, RL, NSL>(t, qq, u);
       if (ok) {
         cplx val = make_double2(x.x * a.scale, x.y * a.scale);
-        if (MODE == FFT_C2R_BWD && scaled) val = make_double2(div_by(val.x, rv, rinv), div_by(val.y, rv, rinv));
+        if (EXT && MODE == FFT_C2R_BWD && scaled) val = make_double2(div_by(val.x, rv, rinv), div_by(val.y, rv, rinv));
         gout[(long long)idx * a.stride_pt] = val;
       }
     }
@@ -336,23 +342,32 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, cplx *sm, long
     const double fac = (double)(2 * N);
     if (t == 0 && ok) {
       cplx val = make_double2(nyq.x * fac, nyq.y * fac);
-      if (scaled) val = make_double2(div_by(val.x, rv, rinv), div_by(val.y, rv, rinv));
+      if (EXT && scaled) val = make_double2(div_by(val.x, rv, rinv), div_by(val.y, rv, rinv));
       gout[(long long)N * a.stride_pt] = val;
     }
   }
 }
 
-template <int MODE, int N, int E, int THREADS>
-__global__ void __launch_bounds__(THREADS) fft_reg_kernel(FftRegArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx *sm = reinterpret_cast<cplx *>(smem_raw);
+// resident CTAs per SM the kernels are compiled for: 5 (4 for c2r) for the plain short-line kernels (48 / 64 registers),
+// 2 for the 16-points-per-thread ones (an explicit 1 lets ptxas take 140-172 registers and halves the occupancy)
+template <int MODE, int N, int THREADS, bool EXT>
+struct MinBlocks {
+  static constexpr int value =
+      THREADS != 256 ? 1 : (N <= 64 ? (EXT ? 3 : (MODE == FFT_C2R_BWD ? 4 : 5)) : 2);
+};
+
+template <int MODE, int N, int E, int THREADS, bool EXT>
+__global__ void __launch_bounds__(THREADS, MinBlocks<MODE, N, THREADS, EXT>::value) fft_reg_kernel(FftRegArgs a) {
+  if (!EXT) {
+    fft_reg_tile<MODE, N, E, THREADS, false>(a, blockIdx.x);   // one tile per CTA
+    return;
+  }
   constexpr int L = THREADS / (N / E);
   const long long ntiles = (a.nlines + L - 1) / L;
-  // plain launches have one tile per CTA; the fused exchange runs a grid-stride loop so that the system-scope fence
-  // that ends it (an NVLink round trip during which the CTA still holds its SM resources) is paid once per CTA,
-  // not once per tile
+  // the fused exchange runs a grid-stride loop so that the system-scope fence that ends it (an NVLink round trip during
+  // which the CTA still holds its SM resources) is paid once per CTA, not once per tile
   for (long long blk = blockIdx.x; blk < ntiles; blk += gridDim.x) {
-    fft_reg_tile<MODE, N, E, THREADS>(a, sm, blk);
+    fft_reg_tile<MODE, N, E, THREADS, true>(a, blk);
     if (blk + gridDim.x < ntiles) __syncthreads();   // the tile's shared buffer is reused
   }
   if (MODE == FFT_R2C_FWD && a.use_peer) dist_finish_put(a.pt, gridDim.x * gridDim.y);
@@ -366,12 +381,12 @@ struct RegCfg {
   static constexpr size_t smem = (size_t)(N + 1) * L * sizeof(cplx);
 };
 
-template <int MODE, int N, int E, int THREADS>
-static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
+template <int MODE, int N, int E, int THREADS, bool EXT>
+static int launch_one_ext(const FftRegArgs &a, int nfields, cudaStream_t st) {
   using C = RegCfg<N, E, THREADS>;
   static bool attr = false;
   if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(fft_reg_kernel<MODE, N, E, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(fft_reg_kernel<MODE, N, E, THREADS, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)C::smem));
     attr = true;
   }
@@ -384,13 +399,23 @@ static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
       CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     int per_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_reg_kernel<MODE, N, E, THREADS>, THREADS, C::smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_reg_kernel<MODE, N, E, THREADS, EXT>, THREADS,
+                                                          C::smem));
     const long long resident = (long long)sms * std::max(per_sm, 1);
     ntiles = std::min(ntiles, std::max(1ll, resident / nfields));
   }
   const dim3 grid((unsigned)ntiles, (unsigned)nfields);
-  fft_reg_kernel<MODE, N, E, THREADS><<<grid, THREADS, C::smem, st>>>(a);
+  fft_reg_kernel<MODE, N, E, THREADS, EXT><<<grid, THREADS, C::smem, st>>>(a);
   return MLEGS_OK;
+}
+
+template <int MODE, int N, int E, int THREADS>
+static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
+  // the extended kernel only exists for the real modes (fused exchange: r2c; fused row scaling: r2c and c2r)
+  if constexpr (MODE == FFT_R2C_FWD || MODE == FFT_C2R_BWD) {
+    if (a.use_peer || a.rs.mode != 0) return launch_one_ext<MODE, N, E, THREADS, true>(a, nfields, st);
+  }
+  return launch_one_ext<MODE, N, E, THREADS, false>(a, nfields, st);
 }
 
 template <int MODE>

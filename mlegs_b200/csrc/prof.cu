@@ -73,7 +73,7 @@ int mlegs_b200_prof_enable(int on) {
 }
 
 // Measured DMMA throughput in TFLOP/s (2 flops per FMA): 16 independent accumulator chains per warp, 8 warps per
-// CTA, 4 CTAs per SM, timed with CUDA events on the library's stream (best of 8 after 12 warm-up launches, ~2.7 ms each).
+// CTA, 4 and 1 CTAs per SM, timed with CUDA events on the library's stream (best of 6 after 8 warm-up launches each).
 int mlegs_b200_dmma_peak(double *tflops) {
   cudaStream_t st = (cudaStream_t)ctx().stream;
   int dev = 0, sms = 0;
@@ -84,21 +84,26 @@ int mlegs_b200_dmma_peak(double *tflops) {
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
-  const int iters = 8192, blocks = sms * 4;
-  // warm-up: the SM clock takes tens of milliseconds of load to settle at its boost state on a fresh box (a single
-  // warm-up launch read 29.7 TFLOP/s on boxes whose next kernels then ran at 32)
-  for (int rep = 0; rep < 12; ++rep) dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
+  // Two occupancies: 32 warps per SM (every box settles near 1965 MHz or, power-limited, near 1570 MHz under this
+  // load) and 8 warps per SM (the DMMA warps of the Legendre kernels; already saturates the pipe,
+  // tools/microbench/dmma_shapes.cu, at a lower power draw).  The peak is the better of the two.
+  const int iters = 8192;
   double best = 0.0;
-  for (int rep = 0; rep < 8; ++rep) {
-    CUDA_TRY(cudaEventRecord(e0, st));
-    dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
-    CUDA_TRY(cudaEventRecord(e1, st));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    double flops = (double)blocks * 8 * iters * 16 * 512.0;   // m8n8k4 = 256 FMA = 512 flops
-    best = std::max(best, flops / (ms * 1e-3) / 1e12);
-    g_launches++;
+  for (int cfg = 0; cfg < 2; ++cfg) {
+    const int blocks = sms * (cfg == 0 ? 4 : 1);
+    // warm-up: the SM clock takes tens of milliseconds of load to settle on a fresh box
+    for (int rep = 0; rep < 8; ++rep) dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
+    for (int rep = 0; rep < 6; ++rep) {
+      CUDA_TRY(cudaEventRecord(e0, st));
+      dmma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
+      CUDA_TRY(cudaEventRecord(e1, st));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      double flops = (double)blocks * 8 * iters * 16 * 512.0;   // m8n8k4 = 256 FMA = 512 flops
+      best = std::max(best, flops / (ms * 1e-3) / 1e12);
+      g_launches++;
+    }
   }
   CUDA_TRY(cudaEventDestroy(e0));
   CUDA_TRY(cudaEventDestroy(e1));
