@@ -541,13 +541,19 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
   for (int sys = blockIdx.x * CSOLVE_WARPS + warp; sys < nsys; sys += gridDim.x * CSOLVE_WARPS) {
     // consecutive systems of a block share the column j (same nn, neighbouring factor storage)
     const int j = sys / a.nk;
-    const int k = a.k0 + sys % a.nk;
+    const int kf = a.k0 + sys % a.nk;     // plane whose factors are used
     const int mglob = a.m0 + j;
     const int nn = nn_of(mglob, a.nrc, a.npc);
     if (nn < 1) continue;
+    const long long c0 = a.fac_off[j] + (long long)(kf - a.k0) * nn;
+   for (int pass = 0; pass < 2; ++pass) {
+    // pass 1: the plane nz - kf has the same operator (ak^2) and therefore the same factors; when the factor set
+    // fits in L2 the second substitution reads them from there instead of HBM
+    if (pass == 0 && a.mirror_mode == 2) continue;
+    const int k = pass == 0 ? kf : a.mirror_nz - kf;
+    if (pass == 1 && (a.mirror_mode == 0 || kf == 0 || k < a.mirror_lo || k >= a.mirror_nz)) break;
     cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
-    const bool special = (a.special00 && mglob == 0 && k == 0);
-    const long long c0 = a.fac_off[j] + (long long)(k - a.k0) * nn;
+    const bool special = (pass == 0 && a.special00 && mglob == 0 && k == 0);
     const double *__restrict__ AB = a.fac_ab + c0 * ldab;
     const unsigned char *__restrict__ piv = a.fac_piv + c0;
     for (int i = lane; i < nn; i += 32) {
@@ -654,6 +660,7 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
     }
     for (int i = lane; i < nn; i += 32) col[i] = make_double2(rhs[2 * i], rhs[2 * i + 1]);
     __syncwarp();
+   }   // pass
   }
 }
 
@@ -693,6 +700,60 @@ static SolveArgs key_of(const SolveArgs &a) {
   k.add_alpha = a.add_alpha; k.alpha = a.alpha; k.beta = a.beta; k.special00 = a.special00;
   k.sp0 = a.sp0; k.sp1 = a.sp1; k.sp2 = a.sp2;   // preln_rhs only enters the right-hand side
   return k;
+}
+
+static bool factor_cached(const SolveArgs &a) {
+  if (!g_fcache_on) return false;
+  SolveArgs key = key_of(a);
+  for (auto &e : g_fcache)
+    if (memcmp(&e.key, &key, sizeof(SolveArgs)) == 0) return true;
+  return false;
+}
+
+// Planes [0, n1) and [lo, nzl) of one operator.  The operator of plane k only contains ak(k)^2 = ak(nz-k)^2, so the
+// second range can be served with the factors of the first: half the factor memory, and -- when the factor set is
+// small enough to survive in L2 between the two substitutions of a warp -- less HBM traffic (128^3: 0.43 -> 0.31 ms
+// per step).  For large factor sets the mirrored substitutions miss L2 and only halve the parallelism (256^3:
+// 1.77 -> 2.14 ms; two right-hand sides through one sweep: 1.90 ms), so there the ranges stay two launches with
+// their own factors.
+int launch_band_solve_ranges(SolveArgs base, int n1, int kl_first, int lo, int nzl, cudaStream_t st) {
+  base.mirror_mode = 0;
+  base.mirror_lo = base.mirror_nz = 0;
+  SolveArgs a = base;
+  a.k0 = 0;
+  a.nk = n1;
+  a.kl = kl_first;
+  SolveArgs b = base;
+  b.k0 = lo;
+  b.nk = nzl - lo;
+  b.special00 = 0;
+  const bool have_a = n1 > 0, have_b = lo < nzl;
+  size_t cols = 0;   // factor columns of the first range
+  for (int j = 0; j < a.npl; ++j) {
+    const int m = a.m0 + j;
+    cols += (size_t)((m < a.npc) ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0) * (size_t)std::max(n1, 0);
+  }
+  const size_t fbytes = cols * (size_t)(2 * a.kl + a.ku + 1) * sizeof(double);
+  // every plane k of the second range has its mirror nz - k inside the first one, same band widths
+  const bool mirrored = have_a && have_b && g_fcache_on && a.kl <= 8 && a.kl == b.kl && lo >= 1 && nzl - lo <= n1 - 1 &&
+                        fbytes <= ((size_t)96 << 20);
+  if (mirrored) {
+    a.mirror_lo = lo;
+    a.mirror_nz = nzl;
+    if (factor_cached(a)) {
+      a.mirror_mode = 1;                       // one launch: (j,k) then (j, nz-k) by the same warp
+      return launch_band_solve(a, st);
+    }
+    MLEGS_TRY(launch_band_solve(a, st));       // factors (and keeps them if memory allows), solves the first range
+    if (factor_cached(a)) {
+      a.mirror_mode = 2;                       // second range from the factors just stored
+      return launch_band_solve(a, st);
+    }
+    return launch_band_solve(b, st);
+  }
+  if (have_a) MLEGS_TRY(launch_band_solve(a, st));
+  if (have_b) MLEGS_TRY(launch_band_solve(b, st));
+  return MLEGS_OK;
 }
 
 int launch_band_solve(SolveArgs a, cudaStream_t st) {

@@ -188,8 +188,14 @@ struct SolveArgs {
   double *fac_ab;                // LAPACK band storage of the LU factors, all systems
   unsigned char *fac_piv;        // pivot offsets jp (0..kl) per column
   const long long *fac_off;      // per local column j: offset (in columns) of system (j, k0); see launch_band_solve
+  // The operator of plane k only contains ak(k)^2 = ak(nz-k)^2: the cached substitution can serve plane nz-k with the
+  // factors of plane k.  mirror_mode 1: every warp solves (j,k) and then (j, nz-k) if mirror_lo <= nz-k < mirror_nz;
+  // 2: the mirrored planes only (launch_band_solve_ranges decides, banded.cu).
+  int mirror_mode, mirror_lo, mirror_nz;
 };
 int launch_band_solve(SolveArgs a, cudaStream_t st);
+// planes [0, n1) and [lo, nzl) of one operator (the two axial loops of the reference's solves)
+int launch_band_solve_ranges(SolveArgs base, int n1, int kl_first, int lo, int nzl, cudaStream_t st);
 void band_solve_cache_clear();
 // 1: solves reuse cached LU factors (default); 0: every call factors again (the reference's behaviour)
 void band_solve_cache_enable(int on);

@@ -339,23 +339,9 @@ int helmp_impl(mlegs_field *s, int power, double alpha, double beta) {
 
 // the two axial loops of the solves (e.g. ops:828-841): planes [0, min(nzl,nzc)) then [max(nzcu,1)-1, nzl)
 static int solve_two_ranges(SolveArgs base, const ChopIdx &ci, int nzl, int kl_first) {
-  int n1 = std::min(nzl, ci.nzc);
-  if (n1 > 0) {
-    SolveArgs a = base;
-    a.k0 = 0;
-    a.nk = n1;
-    a.kl = kl_first;
-    MLEGS_TRY(launch_band_solve(a, strm()));
-  }
-  int lo = std::max(ci.nzcu, 1) - 1;
-  if (lo < nzl) {
-    SolveArgs a = base;
-    a.k0 = lo;
-    a.nk = nzl - lo;
-    a.special00 = 0;
-    MLEGS_TRY(launch_band_solve(a, strm()));
-  }
-  return MLEGS_OK;
+  const int n1 = std::min(nzl, ci.nzc);
+  const int lo = std::max(ci.nzcu, 1) - 1;
+  return launch_band_solve_ranges(base, n1, kl_first, lo, nzl, strm());
 }
 
 static int solve_args(const mlegs_field *s, const ChopIdx &ci, SolveArgs *a) {
