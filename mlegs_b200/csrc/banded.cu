@@ -532,6 +532,9 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
 // ---------------------------------------------------------------------------------------------
 #define CSOLVE_WARPS 8
 
+// MIRROR: the launch also serves the mirrored planes (mirror_mode 1 or 2); compiled separately so that the plain
+// substitution keeps its code (the pass loop cost it 25 % at 256^3 when both lived in one kernel)
+template <bool MIRROR>
 __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -546,12 +549,12 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
     const int nn = nn_of(mglob, a.nrc, a.npc);
     if (nn < 1) continue;
     const long long c0 = a.fac_off[j] + (long long)(kf - a.k0) * nn;
-   for (int pass = 0; pass < 2; ++pass) {
+   for (int pass = 0; pass < (MIRROR ? 2 : 1); ++pass) {
     // pass 1: the plane nz - kf has the same operator (ak^2) and therefore the same factors; when the factor set
     // fits in L2 the second substitution reads them from there instead of HBM
-    if (pass == 0 && a.mirror_mode == 2) continue;
-    const int k = pass == 0 ? kf : a.mirror_nz - kf;
-    if (pass == 1 && (a.mirror_mode == 0 || kf == 0 || k < a.mirror_lo || k >= a.mirror_nz)) break;
+    if (MIRROR && pass == 0 && a.mirror_mode == 2) continue;
+    const int k = (!MIRROR || pass == 0) ? kf : a.mirror_nz - kf;
+    if (MIRROR && pass == 1 && (kf == 0 || k < a.mirror_lo || k >= a.mirror_nz)) break;
     cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
     const bool special = (pass == 0 && a.special00 && mglob == 0 && k == 0);
     const double *__restrict__ AB = a.fac_ab + c0 * ldab;
@@ -781,12 +784,16 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
     size_t smem = (size_t)CSOLVE_WARPS * 2 * a.nnmax * sizeof(double);
     static size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = smem;
     }
     int blocks = (nsys + CSOLVE_WARPS - 1) / CSOLVE_WARPS;
     prof_begin(a.power > 2 ? "ihelmp_solve_cached" : "band_solve_cached", st);
-    band_solve_cached_kernel<<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
+    if (a.mirror_mode != 0)
+      band_solve_cached_kernel<true><<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
+    else
+      band_solve_cached_kernel<false><<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
     prof_end(st);
     KERNEL_CHECK();
     return MLEGS_OK;
