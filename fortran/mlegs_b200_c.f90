@@ -232,6 +232,141 @@ module mlegs_b200_c
       integer(c_signed_char), intent(in) :: handles(*)
       integer(c_int) :: rc
     end function
+    function mlegs_b200_dist_detach() bind(C, name='mlegs_b200_dist_detach') result(rc)
+      import :: c_int
+      integer(c_int) :: rc
+    end function
+    !> MPI_Allreduce(sum) of n host doubles on the library's peer windows (check_stability, vortical_flow_3d.f90:404)
+    function mlegs_b200_dist_allreduce(buf, n) bind(C, name='mlegs_b200_dist_allreduce') result(rc)
+      import :: c_double, c_int
+      real(c_double), intent(inout) :: buf(*)
+      integer(c_int), value :: n
+      integer(c_int) :: rc
+    end function
+    !> one launch per transform stage (and, on several ranks, one fused exchange) for n scalars of the same state;
+    !> `fields` holds c_loc() of the n c_mlegs_field structures
+    function mlegs_b200_trans_many(n, fields, to) bind(C, name='mlegs_b200_trans_many') result(rc)
+      import :: c_ptr, c_char, c_int
+      integer(c_int), value :: n
+      type(c_ptr), intent(in) :: fields(*)
+      character(kind=c_char), intent(in) :: to(*)
+      integer(c_int) :: rc
+    end function
+    !> n host arrays (ordinary s%e storage), H2D + trans + D2H pipelined over PCIe
+    function mlegs_b200_trans_host_batch(n, host_e, from, to, ln) bind(C, name='mlegs_b200_trans_host_batch') result(rc)
+      import :: c_ptr, c_char, c_double, c_int
+      integer(c_int), value :: n
+      type(c_ptr), intent(in) :: host_e(*)
+      character(kind=c_char), intent(in) :: from(*), to(*)
+      real(c_double), intent(in) :: ln(*)
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_set_stream(cuda_stream) bind(C, name='mlegs_b200_set_stream') result(rc)
+      import :: c_ptr, c_int
+      type(c_ptr), value :: cuda_stream
+      integer(c_int) :: rc
+    end function
+    !> visc, hypervisc, svv_* of the module globals changed (timestep_set / read_input re-run)
+    function mlegs_b200_update_params(p) bind(C, name='mlegs_b200_update_params') result(rc)
+      import :: c_mlegs_params, c_int
+      type(c_mlegs_params), intent(in) :: p
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_field_zero(f) bind(C, name='mlegs_b200_field_zero') result(rc)
+      import :: c_mlegs_field, c_int
+      type(c_mlegs_field), intent(inout) :: f
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_field_upload(f, host_e) bind(C, name='mlegs_b200_field_upload') result(rc)
+      import :: c_mlegs_field, c_ptr, c_int
+      type(c_mlegs_field), intent(inout) :: f
+      type(c_ptr), value :: host_e
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_field_download(f, host_e) bind(C, name='mlegs_b200_field_download') result(rc)
+      import :: c_mlegs_field, c_ptr, c_int
+      type(c_mlegs_field), intent(in) :: f
+      type(c_ptr), value :: host_e
+      integer(c_int) :: rc
+    end function
+    !> scalar_chop_offset, mlegs_scalar_init.f90:83-104
+    function mlegs_b200_field_chop_offset(f, iof1, iof2, iof3) bind(C, name='mlegs_b200_field_chop_offset') result(rc)
+      import :: c_mlegs_field, c_int
+      type(c_mlegs_field), intent(inout) :: f
+      integer(c_int), value :: iof1, iof2, iof3
+      integer(c_int) :: rc
+    end function
+    !> helm, ops:762-789 (with the write-back the reference omits)
+    function mlegs_b200_helm(s, alpha) bind(C, name='mlegs_b200_helm') result(rc)
+      import :: c_mlegs_field, c_double, c_int
+      type(c_mlegs_field), intent(inout) :: s
+      real(c_double), value :: alpha
+      integer(c_int) :: rc
+    end function
+    !> abab, ops:1096-1155
+    function mlegs_b200_abab(s, s_p, nl, nl_p, dt, is_2nd_svis_p) bind(C, name='mlegs_b200_abab') result(rc)
+      import :: c_mlegs_field, c_double, c_int
+      type(c_mlegs_field), intent(inout) :: s, s_p, nl, nl_p
+      real(c_double), value :: dt
+      integer(c_int), value :: is_2nd_svis_p
+      integer(c_int) :: rc
+    end function
+    !> y%e = a*y%e + b*x%e: the whole-array expressions of the time loops (vortical_flow_3d.f90:136-137, 379)
+    function mlegs_b200_axpby(y, a, x, b) bind(C, name='mlegs_b200_axpby') result(rc)
+      import :: c_mlegs_field, c_double, c_int
+      type(c_mlegs_field), intent(inout) :: y
+      type(c_mlegs_field), intent(in) :: x
+      real(c_double), value :: a, b
+      integer(c_int) :: rc
+    end function
+    !> all(ieee_is_finite(s%e)), check_stability (vortical_flow_3d.f90:397-409)
+    function mlegs_b200_is_finite(s, all_finite) bind(C, name='mlegs_b200_is_finite') result(rc)
+      import :: c_mlegs_field, c_int
+      type(c_mlegs_field), intent(in) :: s
+      integer(c_int), intent(out) :: all_finite
+      integer(c_int) :: rc
+    end function
+    !> 1: later solves reuse the resident LU factors (default); 0: factor on every call like the reference
+    function mlegs_b200_solve_cache(on) bind(C, name='mlegs_b200_solve_cache') result(rc)
+      import :: c_int
+      integer(c_int), value :: on
+      integer(c_int) :: rc
+    end function
+    !> on-device initial conditions / diagnostics of apps/vortical_flow_3d.f90:258-351, 411-447
+    function mlegs_b200_fill_physical(s, re, im) bind(C, name='mlegs_b200_fill_physical') result(rc)
+      import :: c_mlegs_field, c_double, c_int
+      type(c_mlegs_field), intent(inout) :: s
+      real(c_double), value :: re, im
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_qvort_dist_tp(psi, chi, q, ran_noise, seed) bind(C, name='mlegs_b200_qvort_dist_tp') result(rc)
+      import :: c_mlegs_field, c_double, c_long_long, c_int
+      type(c_mlegs_field), intent(inout) :: psi, chi
+      real(c_double), value :: q, ran_noise
+      integer(c_long_long), value :: seed
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_vort_mag(psi, chi, wr, wp, wz, vormag) bind(C, name='mlegs_b200_vort_mag') result(rc)
+      import :: c_mlegs_field, c_int
+      type(c_mlegs_field), intent(in) :: psi, chi
+      type(c_mlegs_field), intent(inout) :: wr, wp, wz, vormag
+      integer(c_int) :: rc
+    end function
+    !> msave / mload of mlegs_scalar_io.f90 in the reference's binary and formatted layouts (fn is NUL-terminated)
+    function mlegs_b200_msave(s, fn, is_binary, is_global) bind(C, name='mlegs_b200_msave') result(rc)
+      import :: c_mlegs_field, c_char, c_int
+      type(c_mlegs_field), intent(in) :: s
+      character(kind=c_char), intent(in) :: fn(*)
+      integer(c_int), value :: is_binary, is_global
+      integer(c_int) :: rc
+    end function
+    function mlegs_b200_mload(fn, s, is_binary, is_global) bind(C, name='mlegs_b200_mload') result(rc)
+      import :: c_mlegs_field, c_char, c_int
+      character(kind=c_char), intent(in) :: fn(*)
+      type(c_mlegs_field), intent(inout) :: s
+      integer(c_int), value :: is_binary, is_global
+      integer(c_int) :: rc
+    end function
   end interface
 
 contains
