@@ -311,7 +311,9 @@ def run_native(args):
         # scalars one launch of this kernel processes (trans_many: a group per launch)
         per_launch = prof_steps * nfields / v["launches"]
         ent = {"avg_ms": avg_ms, "share": v["ms"] / tot, "launches": v["launches"], "scalars_per_launch": per_launch}
-        base = k.replace("_put", "")     # *_put: the same kernel with the exchange fused into its stores
+        # *_put: the same kernel with the exchange fused into its stores; *_stage / *_ship: the two halves of the
+        # staged (1,2) exchange (rows written locally in destination order, then shipped as long runs)
+        base = k.replace("_put", "").replace("_stage", "").replace("_ship", "")
         ent["alg_GBps"] = per_launch * alg_bytes.get(base, 0) / world / (avg_ms * 1e-3) / 1e9
         ent["hbm_frac"] = ent["alg_GBps"] / hbm_peak
         if k.startswith("legendre"):
@@ -336,7 +338,7 @@ def run_native(args):
     roofline.update({"avg_launch_ms": d["avg_ms"], "share_of_step": d["share"], "dmma_peak_tflops": dmma_peak,
                      "kernels": kernels})
     traffic_file = os.path.join(ROOT, "profiles", "r1", "traffic.json")
-    if os.path.exists(traffic_file) and world == 1:
+    if os.path.exists(traffic_file) and world == 1 and SHAPE is None:
         tr = json.load(open(traffic_file)).get(str(args.size), {})
         per_field = tr.get(dom)
         roofline["traffic"] = per_field * d["scalars_per_launch"] if per_field is not None else None
