@@ -262,7 +262,10 @@ int launch_band_op(const BandOpArgs &a, cudaStream_t st) {
   }
   dim3 grid(a.npl, (a.nzl + KB - 1) / KB);
   int threads = std::min(1024, (a.nrl + 31) / 32 * 32);
-  prof_begin(a.combine ? "helmp_band" : (a.nb == 3 ? "xxdx_band" : "del2_band"), st);
+  // one pass over the retained lines (helmp's whole-array combination touches every line of the block)
+  const double lines_b = a.combine ? (double)a.nrl * a.npl * a.nzl
+                                   : retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu);
+  prof_begin(a.combine ? "helmp_band" : (a.nb == 3 ? "xxdx_band" : "del2_band"), st, 32.0 * lines_b);
   if (a.nb == 3)
     band_op_kernel<3><<<grid, threads, smem, st>>>(a, KB);
   else
@@ -789,7 +792,16 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
       attr_set = smem;
     }
     int blocks = (nsys + CSOLVE_WARPS - 1) / CSOLVE_WARPS;
-    prof_begin(a.power > 2 ? "ihelmp_solve_cached" : "band_solve_cached", st);
+    // algorithmic bytes: the factor stream (ldab doubles + one pivot byte per matrix column, read once -- the
+    // mirrored plane re-reads it from L2) + one read and one write of every right-hand side
+    double syscols = 0.0;
+    for (int j = 0; j < a.npl; ++j) {
+      const int m = a.m0 + j;
+      syscols += (double)((m < a.npc) ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0) * a.nk;
+    }
+    const double rhs_cols = a.mirror_mode == 1 ? 2.0 * syscols : syscols;
+    prof_begin(a.power > 2 ? "ihelmp_solve_cached" : "band_solve_cached", st,
+               syscols * (ldab * 8.0 + 1.0) + 32.0 * rhs_cols);
     if (a.mirror_mode != 0)
       band_solve_cached_kernel<true><<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
     else
@@ -811,12 +823,18 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
     const size_t need = ncols * ldab * sizeof(double) + ncols + off.size() * sizeof(long long);
     size_t freeb = 0, totalb = 0;
     cudaMemGetInfo(&freeb, &totalb);
-    // evict least recently used entries until the new one fits in half of the free memory
-    while (!g_fcache.empty() && need > freeb / 2) {
+    // The cache is keyed on the exact (alpha, beta): a caller that varies dt adds a factor set per step.  Bound it by
+    // entry count and by a byte budget (a third of the device memory) as well as by what is free right now, evicting
+    // least recently used entries first.
+    const size_t kMaxEntries = 12;
+    size_t held = 0;
+    for (auto &e : g_fcache) held += e.bytes;
+    while (!g_fcache.empty() && (need > freeb / 2 || g_fcache.size() >= kMaxEntries || held + need > totalb / 3)) {
       size_t lru = 0;
       for (size_t i = 1; i < g_fcache.size(); ++i)
         if (g_fcache[i].stamp < g_fcache[lru].stamp) lru = i;
       CUDA_TRY(cudaStreamSynchronize(st));
+      held -= g_fcache[lru].bytes;
       free_entry(g_fcache[lru]);
       g_fcache.erase(g_fcache.begin() + lru);
       cudaMemGetInfo(&freeb, &totalb);

@@ -16,6 +16,7 @@
 // bit-identical results.
 #include <algorithm>
 #include <cstring>
+#include <string>
 
 #include "dist_dev.cuh"
 
@@ -195,13 +196,15 @@ int exchange_slab(mlegs_field *s, int axis_old, int axis_new, const void *src, v
   return MLEGS_OK;
 }
 
+// Host-side completion check of everything queued so far, including exchange barriers: a barrier that waited ~10 minutes
+// for a dead peer traps (dist_dev.cuh), which surfaces here -- and at every later CUDA call -- as a launch failure.
 int dist_check_timeout() {
   Context &c = ctx();
   if (c.nranks == 1) return MLEGS_OK;
-  int h[4] = {0, 0, 0, 0};
-  CUDA_TRY(cudaMemcpyAsync(h, c.d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)c.stream));
-  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)c.stream));
-  if (h[2]) return fail(MLEGS_E_COMM, "scalar_exchange: timed out waiting for a peer rank");
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)c.stream);
+  if (e != cudaSuccess)
+    return fail(MLEGS_E_COMM, std::string("scalar_exchange: exchange barrier failed (a peer rank never arrived): ") +
+                                  cudaGetErrorString(e));
   return MLEGS_OK;
 }
 

@@ -8,7 +8,10 @@ namespace mlegs {
 #define DIST_MAX_RANKS 16
 #define DIST_FLAG_BYTES 4096
 #define DIST_RED_DOUBLES 16384                      // per rank and parity (>= 2 nz)
-#define DIST_SPIN_LIMIT (1ll << 31)                 // ~1-2 s of clock64 ticks before giving up
+// A rank may legitimately be seconds late to an exchange (a checkpoint write, a first-use factorisation, the host table
+// build, Python GC), so waiting never gives up with a wrong answer: the poll backs off and, after ~10 minutes of
+// clock64 ticks (a dead peer), traps -- the context dies and every later CUDA call of this rank reports it.
+#define DIST_SPIN_LIMIT (1ll << 40)
 
 struct WinHeader {                                  // lives at the start of every window
   unsigned long long arrive[DIST_MAX_RANKS];        // data barrier: epoch published by rank q
@@ -90,10 +93,16 @@ __device__ __forceinline__ void barrier_publish_wait(const PeerTable &t, bool re
     WinHeader *me = reinterpret_cast<WinHeader *>(t.base[t.rank]);
     const unsigned long long *p = reduction ? &me->red_arrive[q] : &me->arrive[q];
     const long long t0 = clock64();
+    unsigned backoff = 0;
     while (ld_acquire_sys(p) < t.epoch) {
-      if (clock64() - t0 > DIST_SPIN_LIMIT) {
-        atomicOr(t.flag + 2, 1);
-        break;
+      if (backoff < 4096u) {
+        ++backoff;                       // the first microseconds: poll at full rate (the common case)
+      } else {
+        __nanosleep(1000);               // a late peer: one poll per microsecond keeps NVLink and the LSU free
+        if (clock64() - t0 > DIST_SPIN_LIMIT) {
+          atomicOr(t.flag + 2, 1);
+          __trap();                      // never continue past an incomplete barrier
+        }
       }
     }
   }

@@ -3,6 +3,7 @@
 // Reference: /root/reference/src/submodules/mlegs_scalar_ops.f90:6-155, 237-416, 1264-1306.
 // All HBM-bound; compiled with -fmad=false so that every product/sum rounds like the reference's
 // (non-fused) Fortran expressions.
+#include <algorithm>
 #include <cmath>
 
 #include "kernels.h"
@@ -47,7 +48,26 @@ __global__ void mask_kernel(MaskArgs a) {
 int launch_mask(const MaskArgs &a, cudaStream_t st) {
   size_t n = (size_t)a.nrl * a.npl * a.nzl;
   if (!n) return MLEGS_OK;
-  prof_begin("mask", st);
+  // write-only: 16 bytes per zeroed element
+  double zeroed = 0.0;
+  {
+    int kzm = 0;
+    for (int k = 0; k < a.nzl; ++k) kzm += (k >= a.kz_lo && k < a.kz_hi) ? 1 : 0;
+    for (int j = 0; j < a.npl; ++j) {
+      const int m = a.m0 + j;
+      if (m >= a.col_cut) {
+        zeroed += (double)a.nrl * a.nzl;
+        continue;
+      }
+      int rz = 0;
+      if (a.row_mode) {
+        int nn = m < a.npc_rows ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
+        rz = a.nrl - std::min(std::max(nn - a.r0, 0), a.nrl);
+      }
+      zeroed += (double)kzm * a.nrl + (double)(a.nzl - kzm) * rz;
+    }
+  }
+  prof_begin("mask", st, 16.0 * zeroed);
   mask_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(a);
   prof_end(st);
   KERNEL_CHECK();
@@ -142,7 +162,7 @@ int launch_svv_energy(const SvvArgs &a, double *d_partial, double *d_out2, cudaS
   size_t n = (size_t)a.nrl * a.npl * a.nzl;
   unsigned g = ew_grid(n);
   if (g > SVV_BLOCKS) g = SVV_BLOCKS;
-  prof_begin("svv_energy", st);
+  prof_begin("svv_energy", st, 16.0 * (double)n);
   svv_energy_kernel<<<g, EW_THREADS, 0, st>>>(a, d_partial);
   prof_end(st);
   KERNEL_CHECK();
@@ -197,7 +217,7 @@ __global__ void calcat_kernel(cplx *e, int nrl, int npl, int nrows, const double
 
 int launch_calcat(cplx *e, int nrl, int npl, int nzl, int nrows, const double *at, cplx *out, int subtract,
                   double at_first, cudaStream_t st) {
-  prof_begin("calcat", st);
+  prof_begin("calcat", st, 16.0 * (double)nrows * nzl);
   calcat_kernel<<<nzl, EW_THREADS, 0, st>>>(e, nrl, npl, nrows, at, out, subtract, at_first);
   prof_end(st);
   KERNEL_CHECK();
@@ -238,7 +258,7 @@ __global__ void delsqp_kernel(cplx *e, int nrl, int npl, int nzl, int m0, int nr
 int launch_delsqp(cplx *e, int nrl, int npl, int nzl, int m0, int nrc, int npc, double ell2, int inverse,
                   cudaStream_t st) {
   size_t n = (size_t)nrl * npl * nzl;
-  prof_begin(inverse ? "idelsqp" : "delsqp", st);
+  prof_begin(inverse ? "idelsqp" : "delsqp", st, 32.0 * retained_elems(nrl, npl, nzl, 0, m0, nrc, npc, nzl, nzl));
   delsqp_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(e, nrl, npl, nzl, m0, nrc, npc, ell2, inverse);
   prof_end(st);
   KERNEL_CHECK();
@@ -303,7 +323,7 @@ __global__ void vecprod_kernel(cplx *vr, cplx *vp, cplx *vz, const cplx *ur, con
 int launch_vecprod(cplx *vr, cplx *vp, cplx *vz, const cplx *ur, const cplx *up, const cplx *uz, int nrl, int npl,
                    int nzl, int r0, int nr, int nph, int nz, cudaStream_t st) {
   size_t n = (size_t)nrl * npl * nzl;
-  prof_begin("vecprod", st);
+  prof_begin("vecprod", st, 9.0 * 16.0 * (double)n);   // 6 fields read, 3 written
   vecprod_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(vr, vp, vz, ur, up, uz, nrl, npl, nzl, r0, nr, nph, nz);
   prof_end(st);
   KERNEL_CHECK();
@@ -325,7 +345,8 @@ int launch_vecprod(cplx *vr, cplx *vp, cplx *vz, const cplx *ur, const cplx *up,
 
 __global__ void lincomb_kernel(LinArgs p) {
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.n; idx += (size_t)gridDim.x * blockDim.x) {
-    cplx y = p.y[idx], o;
+    cplx y = make_double2(0.0, 0.0), o;
+    if (p.mode != 2 && p.mode != 3 && p.mode != 6) y = p.y[idx];   // out-of-place modes never read the destination
     switch (p.mode) {
       case 0: {
         cplx x = p.x1[idx];
@@ -378,7 +399,9 @@ __global__ void lincomb_kernel(LinArgs p) {
 
 int launch_lincomb(const LinArgs &p, cudaStream_t st) {
   if (!p.n) return MLEGS_OK;
-  prof_begin("lincomb", st);
+  // fields read (incl. y where the mode needs it) + one written
+  static const int reads[9] = {2, 2, 2, 3, 1, 2, 3, 3, 5};
+  prof_begin("lincomb", st, 16.0 * (double)p.n * (reads[p.mode < 0 || p.mode > 8 ? 7 : p.mode] + 1));
   lincomb_kernel<<<ew_grid(p.n), EW_THREADS, 0, st>>>(p);
   prof_end(st);
   KERNEL_CHECK();
@@ -400,7 +423,7 @@ __global__ void rscale_kernel(cplx *e, int nrl, size_t ncols, int r0, int nr, co
 }
 int launch_rscale(cplx *e, int nrl, size_t ncols, int r0, int nr, const double *r, int divide, cudaStream_t st) {
   size_t n = (size_t)nrl * ncols;
-  prof_begin("rscale", st);
+  prof_begin("rscale", st, 32.0 * (double)nrl * ncols);
   rscale_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(e, nrl, ncols, r0, nr, r, divide);
   prof_end(st);
   KERNEL_CHECK();
@@ -465,7 +488,8 @@ __global__ void tp_combine_kernel(TpCombineArgs a) {
 }
 int launch_tp_combine(const TpCombineArgs &a, cudaStream_t st) {
   size_t n = (size_t)a.nrl * a.npl * a.nzl;
-  prof_begin("tp_combine", st);
+  prof_begin("tp_combine", st, ((a.mode == 0 || a.mode == 2) ? 32.0 : 48.0) *
+                                   retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu));
   tp_combine_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(a);
   prof_end(st);
   KERNEL_CHECK();
@@ -513,7 +537,7 @@ __global__ void tv_combine_kernel(TvCombineArgs a) {
 }
 int launch_tv_combine(const TvCombineArgs &a, cudaStream_t st) {
   size_t n = (size_t)a.nrl * a.npl * a.nzl;
-  prof_begin("tv_combine", st);
+  prof_begin("tv_combine", st, 96.0 * retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu));
   tv_combine_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(a);
   prof_end(st);
   KERNEL_CHECK();

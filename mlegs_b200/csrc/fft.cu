@@ -268,8 +268,13 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
                                  scale, st, nullptr));
     return MLEGS_OK;
   }
+  // algorithmic bytes: a c2c line moves 2 x 16 N bytes; an r2c / c2r line 16 N (the packed reals) + 16 (N + 1)
+  const double nfld = (fb && fb->n > 0) ? fb->n : 1;
+  const bool is_phi = mode == FFT_R2C_FWD || mode == FFT_C2R_BWD;
+  const double line_bytes = is_phi ? 16.0 * plan.n + 16.0 * (plan.n + 1) : 32.0 * plan.n;
+  const double alg_bytes = nfld * (double)batch0 * batch1 * line_bytes;
   if (fft_reg_supported(plan.n)) {
-    prof_begin(names[(int)mode], st);
+    prof_begin(names[(int)mode], st, alg_bytes);
     int rc = launch_fft_reg(mode, plan.n, in, out, batch0 * batch1, batch0, stride_b1, stride_pt, tw, tw_order, scale,
                             nullptr, 0, 0, st, nullptr, 0, fb, rs);
     prof_end(st);
@@ -282,7 +287,7 @@ int launch_fft_lines(FftMode mode, const FftPlan &plan, const cplx *in, cplx *ou
   for (int i = 0; i < FFT_MAXPASS; ++i) pl.radix[i] = plan.radix[i];
   dim3 grid((unsigned)((batch0 + plan.ti - 1) / plan.ti), (unsigned)batch1);
   const cplx *twc = reinterpret_cast<const cplx *>(tw);
-  prof_begin(names[(int)mode], st);
+  prof_begin(names[(int)mode], st, alg_bytes);
   switch (mode) {
     case FFT_C2C_FWD:
       fft_lines_kernel<FFT_C2C_FWD><<<grid, FFT_THREADS, plan.smem, st>>>(in, out, plan.n, plan.ti, batch0, stride_pt,
@@ -310,7 +315,8 @@ int launch_fft_phi_forward_put(const FftPlan &plan, const cplx *in, long long ro
                                const double *tw, int tw_order, double scale, const PeerTable &peer, int nrdim,
                                cudaStream_t st, const FieldBatch *fb, const RowScale *rs) {
   if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: the fused exchange needs the register kernels");
-  prof_begin("fft_phi_forward_put", st);
+  prof_begin("fft_phi_forward_put", st,
+             ((fb && fb->n > 0) ? fb->n : 1) * (double)rows * nz * (16.0 * plan.n + 16.0 * (plan.n + 1)));
   int rc = launch_fft_reg(FFT_R2C_FWD, plan.n, in, nullptr, rows * nz, rows, plane, rows, tw, tw_order, scale, nullptr, 0, 0,
                           st, &peer, nrdim, fb, rs);
   prof_end(st);
@@ -324,7 +330,8 @@ int launch_fft_z_compact(FftMode mode, const FftPlan &plan, const cplx *in, cplx
                          cudaStream_t st, const FieldBatch *fb) {
   if (nlines <= 0) return MLEGS_OK;
   if (!fft_reg_supported(plan.n)) return fail(MLEGS_E_STATE, "fft: compact mode needs the register kernels");
-  prof_begin(mode == FFT_C2C_FWD ? "fft_z_forward" : "fft_z_backward", st);
+  prof_begin(mode == FFT_C2C_FWD ? "fft_z_forward" : "fft_z_backward", st,
+             ((fb && fb->n > 0) ? fb->n : 1) * (double)nlines * 32.0 * plan.n);
   int rc = launch_fft_reg(mode, plan.n, in, out, nlines, 1, 0, stride_pt, tw, tw_order, scale, colstart, ncols, nrl, st,
                           nullptr, 0, fb);
   prof_end(st);

@@ -290,15 +290,15 @@ int mload_part(const char *fn, mlegs_field *s, cplx *host_e, int is_binary, int 
     const int *got = is_global ? hdr : hdr + 3;
     if (got[0] != L.n1 || got[1] != L.n2 || got[2] != L.n3) rc = size_error(got);
   }
-  char tok[128];
+  char tok[128] = "0";
   for (int k = 0; k < L.n3 && rc == MLEGS_OK; ++k)
     for (int i = 0; i < L.n1 && rc == MLEGS_OK; ++i)
       for (int j = 0; j < L.n2 && rc == MLEGS_OK; ++j) {
-        double re, im;
+        double re = 0.0, im = 0.0;
         if (fscanf(fp, "%127s", tok) != 1) rc = io_fail("mload_scalar: unexpected end of", name.c_str());
-        re = strtod(tok, nullptr);
+        if (rc == MLEGS_OK) re = strtod(tok, nullptr);
         if (rc == MLEGS_OK && fscanf(fp, "%127s", tok) != 1) rc = io_fail("mload_scalar: unexpected end of", name.c_str());
-        im = strtod(tok, nullptr);
+        if (rc == MLEGS_OK) im = strtod(tok, nullptr);
         const int li = i - i0, lj = j - j0, lk = k - k0;
         if (rc == MLEGS_OK && li >= 0 && li < l1 && lj >= 0 && lj < l2 && lk >= 0 && lk < l3)
           host_e[((size_t)lk * l2 + lj) * l1 + li] = make_double2(re, im);
@@ -323,11 +323,16 @@ int mload_part(const char *fn, mlegs_field *s, cplx *host_e, int is_binary, int 
   return rc;
 }
 
+int dist_check_timeout();                     // dist.cu: stream synchronize + barrier failure report
+
+// MPI_Barrier(comm_glb) of mlegs_scalar_io.f90:79 as a HOST barrier: the device all-reduce only completes once every
+// rank has entered it, and the host waits for it here -- no rank touches the file before rank 0 has laid it out.
 static int barrier_ranks() {
   Context &c = ctx();
   if (c.nranks <= 1) return MLEGS_OK;
   CUDA_TRY(cudaMemsetAsync(c.d_red, 0, sizeof(double), (cudaStream_t)c.stream));
-  return dist_allreduce(c.d_red, 1);
+  MLEGS_TRY(dist_allreduce(c.d_red, 1));
+  return dist_check_timeout();
 }
 
 }  // namespace mlegs

@@ -30,8 +30,25 @@ struct RowScale {
 };
 
 // prof.cu: optional CUDA-event timing around each launch
-void prof_begin(const char *name, cudaStream_t st);
+// bytes / flops: the ALGORITHMIC HBM bytes and floating-point operations of this launch, summed
+// per kernel name in the report so that bench.py can quote achieved GB/s and TFLOP/s for every kernel class
+void prof_begin(const char *name, cudaStream_t st, double bytes = 0.0, double flops = 0.0);
 void prof_end(cudaStream_t st);
+
+// elements (n, m, k) of a local (nrl, npl, nzl) spectral block that the truncation keeps: rows r0 + i < nn(m) of the
+// columns m0 + j < npc, planes k < nzc or k >= nzcu (host helper of the algorithmic-byte counts above)
+inline double retained_elems(int nrl, int npl, int nzl, int r0, int m0, int nrc, int npc, int nzc, int nzcu) {
+  double rows = 0.0;
+  for (int j = 0; j < npl; ++j) {
+    const int m = m0 + j;
+    int nn = m < npc ? (nrc < nrc - m ? nrc : nrc - m) : 0;
+    nn -= r0;
+    rows += nn < 0 ? 0 : (nn > nrl ? nrl : nn);
+  }
+  int planes = 0;
+  for (int k = 0; k < nzl; ++k) planes += (k < nzc || k >= nzcu) ? 1 : 0;
+  return rows * planes;
+}
 
 // ---- fft.cu ----------------------------------------------------------------------------
 int make_fft_plan(int n_complex, int extra_points, FftPlan *plan);

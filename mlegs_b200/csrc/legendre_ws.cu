@@ -706,6 +706,23 @@ bool leg_ws_supported(const LegArgs &a) { return (a.nrh & 1) == 0; }
 
 int launch_slab_ship(const PeerTable &t, const FieldBatch &fb, cudaStream_t st);   // dist.cu
 
+// Algorithmic work of one radial transform launch: flops 2 nr nz S with S = sum of nn(m) over the
+// local columns (parity-folded real table x complex data); bytes 16 nr nz per column with work + 16 S nz.
+void leg_alg_work(const LegArgs &a, double *bytes, double *flops) {
+  double S = 0.0, cols = 0.0;
+  for (int ml = 0; ml < a.npl; ++ml) {
+    const int m = a.m0 + ml;
+    const int nn = m < a.npc ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
+    if (nn > 0 && !(a.skip_m0 && m == 0)) {
+      S += nn;
+      cols += 1.0;
+    }
+  }
+  const double nf = a.fb.n > 0 ? a.fb.n : 1;
+  *flops = nf * 2.0 * a.nr * a.nzl * S;
+  *bytes = nf * (16.0 * a.nr * cols * a.nzl + 16.0 * S * a.nzl);
+}
+
 // `a` has its batch filled in (legendre.cu: with_batch)
 int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   MLEGS_TRY(ws_setup());
@@ -731,7 +748,9 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   static const char *force = getenv("MLEGS_EXCHANGE12");   // "stage" / "put": A/B timing
   bool stage = a.peer && a.fb.out[0] != nullptr && (a.nrdim / a.peer->nranks) < 48;
   if (a.peer && a.fb.out[0] != nullptr && force) stage = force[0] == 's';
-  prof_begin(a.peer ? (stage ? "legendre_backward_stage" : "legendre_backward_put") : "legendre_backward", st);
+  double wb = 0.0, wf = 0.0;
+  leg_alg_work(a, &wb, &wf);
+  prof_begin(a.peer ? (stage ? "legendre_backward_stage" : "legendre_backward_put") : "legendre_backward", st, wb, wf);
   if (stage) {
     leg_backward_ws_kernel<2><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
   } else if (a.peer) {
@@ -781,7 +800,9 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   const int grid = std::max(1, std::min(g_ws_sms, std::max(total, 1)));
   LegArgs b = a;
   b.pf = tab;
-  prof_begin("legendre_forward", st);
+  double wb = 0.0, wf = 0.0;
+  leg_alg_work(a, &wb, &wf);
+  prof_begin("legendre_forward", st, wb, wf);
   leg_forward_ws_kernel<<<grid, WS_THREADS, sizeof(FwdSmemWS), st>>>(b, L, *tm);
   prof_end(st);
   KERNEL_CHECK();

@@ -11,6 +11,7 @@ namespace mlegs {
 struct ProfRec {
   const char *name;
   cudaEvent_t a, b;
+  double bytes, flops;
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_recs;
@@ -27,10 +28,12 @@ static cudaEvent_t get_event() {
   return e;
 }
 
-void prof_begin(const char *name, cudaStream_t st) {
+void prof_begin(const char *name, cudaStream_t st, double bytes, double flops) {
   if (!g_prof_on) return;
   ProfRec r;
   r.name = name;
+  r.bytes = bytes;
+  r.flops = flops;
   r.a = get_event();
   r.b = get_event();
   cudaEventRecord(r.a, st);
@@ -112,16 +115,23 @@ int mlegs_b200_dmma_peak(double *tflops) {
   return MLEGS_OK;
 }
 
-// Writes a JSON object {"kernel": {"launches": n, "ms": total}, ...} and clears the records.
+// Writes a JSON object {"kernel": {"launches": n, "ms": total, "bytes": algorithmic, "flops": algorithmic}, ...} and
+// clears the records.
 int mlegs_b200_prof_report(char *buf, size_t nbuf) {
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ctx().stream));
-  std::map<std::string, std::pair<long long, double>> agg;
+  struct Agg {
+    long long n = 0;
+    double ms = 0.0, bytes = 0.0, flops = 0.0;
+  };
+  std::map<std::string, Agg> agg;
   for (auto &r : g_recs) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
     auto &p = agg[r.name];
-    p.first += 1;
-    p.second += ms;
+    p.n += 1;
+    p.ms += ms;
+    p.bytes += r.bytes;
+    p.flops += r.flops;
     g_pool.push_back(r.a);
     g_pool.push_back(r.b);
   }
@@ -129,9 +139,9 @@ int mlegs_b200_prof_report(char *buf, size_t nbuf) {
   std::string out = "{";
   bool first = true;
   for (auto &kv : agg) {
-    char tmp[256];
-    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
-             kv.second.first, kv.second.second);
+    char tmp[384];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"bytes\": %.0f, \"flops\": %.0f}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
     out += tmp;
     first = false;
   }

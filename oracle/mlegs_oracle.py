@@ -704,26 +704,70 @@ def idelsqp(s: Scalar, kit: Kit):
     s.e, s.ln = so.e, so.ln
 
 
+# The per-(m,k) sweeps below (ops:442-449, 544-558, 600-668, 700-758, 828-852, 953-984) are independent per azimuthal
+# column m.  set_workers(n > 1) runs the columns of one sweep on n forked processes -- the same function on the same
+# column data, so results are bit-identical to the serial sweep (tests/test_oracle_analytic.py checks that); it only
+# makes the 64^3 / 128^3 time-step parity tests affordable.  Never call it in a process that has initialised CUDA.
+_WORKERS = 1
+_SWEEP = None
+
+
+def set_workers(n: int):
+    global _WORKERS
+    _WORKERS = max(1, int(n))
+
+
+def _sweep_task(mm: int):
+    body, e = _SWEEP
+    col = np.array(e[:, mm, :], order="F")
+    aux = body(mm, col)
+    return mm, col, aux
+
+
+def _sweep_columns(s: Scalar, cols, body) -> dict:
+    """body(mm, col) updates col = s.e[:, mm, :] in place and returns an auxiliary value (or None).  Returns {mm: aux}."""
+    global _SWEEP
+    cols = list(cols)
+    if _WORKERS <= 1 or len(cols) < 2:
+        return {mm: body(mm, s.e[:, mm, :]) for mm in cols}
+    import multiprocessing as mp
+    _SWEEP = (body, s.e)
+    try:
+        with mp.get_context("fork").Pool(min(_WORKERS, len(cols))) as pool:
+            out = pool.map(_sweep_task, cols, chunksize=1)
+    finally:
+        _SWEEP = None
+    aux = {}
+    for mm, col, a in out:
+        s.e[:, mm, :] = col
+        aux[mm] = a
+    return aux
+
+
 def _apply_band_per_mk(s: Scalar, kit: Kit, builder, per_k: bool):
     """Shared loop of xxdx/del2h/del2 (ops:442-449, 489-503, 544-558): the operator acts on rows
     :nn of every retained (m,k) column, first k-range then second k-range."""
     ci = chop_index(s, kit)
     first, second = k_ranges(ci, s.e.shape[2])
-    for mm in range(min(s.e.shape[1], ci.npc)):
+
+    def body(mm, col):
         nn = int(ci.nrcs[mm])
         if nn < 1:
-            continue
+            return None
         mval = int(kit.m[mm])
         if not per_k:
             band = builder(mval, 0.0, nn)
             for rng in (first, second):
                 if rng:
-                    s.e[:nn, mm, rng[0]: rng[-1] + 1] = band_mulvec(band, s.e[:nn, mm, rng[0]: rng[-1] + 1])
+                    col[:nn, rng[0]: rng[-1] + 1] = band_mulvec(band, col[:nn, rng[0]: rng[-1] + 1])
         else:
             for rng in (first, second):
                 for kk in rng:
                     band = builder(mval, float(kit.ak[kk]), nn)
-                    s.e[:nn, mm, kk] = band_mulvec(band, s.e[:nn, mm, kk])
+                    col[:nn, kk] = band_mulvec(band, col[:nn, kk])
+        return None
+
+    _sweep_columns(s, range(min(s.e.shape[1], ci.npc)), body)
 
 
 def xxdx(s: Scalar, kit: Kit):
@@ -773,11 +817,12 @@ def idel2_proln(s: Scalar, kit: Kit):
     _require_fff(s, kit)
     ell = kit.p.ell
     first, second = k_ranges(ci, s.e.shape[2])
-    ln = s.ln
-    for mm in range(min(s.e.shape[1], ci.npc)):
+
+    def body(mm, col):
+        ln = None
         nn = int(ci.nrcs[mm])
         if nn < 1:
-            continue
+            return ln
         mval = int(kit.m[mm])
         for ir, rng in enumerate((first, second)):
             for kk in rng:
@@ -786,11 +831,15 @@ def idel2_proln(s: Scalar, kit: Kit):
                     band[0][0] = band[0][0] + 4.0 / 3.0 / ell ** 2.0
                     band[-1][1] = band[-1][1] - 2.0 / 1.0 / ell ** 2.0 * math.exp(kit.lognorm[0, 0] - kit.lognorm[1, 0])
                     band[-2][2] = band[-2][2] + 2.0 / 3.0 / ell ** 2.0 * math.exp(kit.lognorm[0, 0] - kit.lognorm[2, 0])
-                    s.e[:nn, mm, kk] = band_lsolve(band, nn, 2, 2, s.e[:nn, mm, kk])
-                    ln = float((s.e[0, mm, kk] * math.exp(kit.lognorm[0, 0])).real)
+                    col[:nn, kk] = band_lsolve(band, nn, 2, 2, col[:nn, kk])
+                    ln = float((col[0, kk] * math.exp(kit.lognorm[0, 0])).real)
                 else:
-                    s.e[:nn, mm, kk] = band_lsolve(band, nn, 2, 2, s.e[:nn, mm, kk])
-    s.ln = ln
+                    col[:nn, kk] = band_lsolve(band, nn, 2, 2, col[:nn, kk])
+        return ln
+
+    aux = _sweep_columns(s, range(min(s.e.shape[1], ci.npc)), body)
+    if aux.get(0) is not None:
+        s.ln = aux[0]
 
 
 def idel2_preln(s: Scalar, kit: Kit, preln: float):
@@ -799,11 +848,12 @@ def idel2_preln(s: Scalar, kit: Kit, preln: float):
     _require_fff(s, kit)
     ell = kit.p.ell
     first, second = k_ranges(ci, s.e.shape[2])
-    ln = s.ln
-    for mm in range(min(s.e.shape[1], ci.npc)):
+
+    def body(mm, col):
+        ln = None
         nn = int(ci.nrcs[mm])
         if nn < 1:
-            continue
+            return ln
         mval = int(kit.m[mm])
         for ir, rng in enumerate((first, second)):
             for kk in rng:
@@ -829,14 +879,18 @@ def idel2_preln(s: Scalar, kit: Kit, preln: float):
                         v = np.zeros(nn)
                         v[ok] = full[i[ok], j[ok]]
                         b2[d] = v
-                    rhs = s.e[:nn, mm, kk].copy()
-                    rhs[1:nn] = s.e[0:nn - 1, mm, kk]
+                    rhs = col[:nn, kk].copy()
+                    rhs[1:nn] = col[0:nn - 1, kk]
                     rhs[0] = preln / math.exp(kit.lognorm[0, 0])
-                    s.e[:nn, mm, kk] = band_lsolve(b2, nn, 3, 2, rhs)
-                    ln = float((s.e[0, mm, kk] * math.exp(kit.lognorm[0, 0])).real)
+                    col[:nn, kk] = band_lsolve(b2, nn, 3, 2, rhs)
+                    ln = float((col[0, kk] * math.exp(kit.lognorm[0, 0])).real)
                 else:
-                    s.e[:nn, mm, kk] = band_lsolve(band, nn, 2, 2, s.e[:nn, mm, kk])
-    s.ln = ln
+                    col[:nn, kk] = band_lsolve(band, nn, 2, 2, col[:nn, kk])
+        return ln
+
+    aux = _sweep_columns(s, range(min(s.e.shape[1], ci.npc)), body)
+    if aux.get(0) is not None:
+        s.ln = aux[0]
 
 
 def ihelm(s: Scalar, alpha: float, kit: Kit):
@@ -851,16 +905,20 @@ def ihelm(s: Scalar, alpha: float, kit: Kit):
     s.e[1, 0, 0] = s.e[1, 0, 0] + c1 * s.ln
     s.e[2, 0, 0] = s.e[2, 0, 0] - c2 * s.ln
     first, second = k_ranges(ci, s.e.shape[2])
-    for mm in range(min(s.e.shape[1], ci.npc)):
+
+    def body(mm, col):
         nn = int(ci.nrcs[mm])
         if nn < 1:
-            continue
+            return None
         mval = int(kit.m[mm])
         for rng in (first, second):
             for kk in rng:
                 band = leg_del2(mval, float(kit.ak[kk]), nn, kit)
                 band[0] = band[0] + alpha
-                s.e[:nn, mm, kk] = band_lsolve(band, nn, 2, 2, s.e[:nn, mm, kk])
+                col[:nn, kk] = band_lsolve(band, nn, 2, 2, col[:nn, kk])
+        return None
+
+    _sweep_columns(s, range(min(s.e.shape[1], ci.npc)), body)
 
 
 def helmp(s: Scalar, power: int, alpha: float, beta: float, kit: Kit):
@@ -917,15 +975,19 @@ def ihelmp(s: Scalar, power: int, alpha: float, beta: float, kit: Kit):
         bl = band_mulvec(d2_00, bl.astype(np.complex128)).real
     s.e[:nrc, 0, 0] = s.e[:nrc, 0, 0] - bl - beta * bl2
     first, second = k_ranges(ci, s.e.shape[2])
-    for mm in range(min(s.e.shape[1], ci.npc)):
+
+    def body(mm, col):
         nn = int(ci.nrcs[mm])
         if nn < 1:
-            continue
+            return None
         mval = int(kit.m[mm])
         for rng in (first, second):
             for kk in rng:
                 band = helmp_band(mval, float(kit.ak[kk]), nn, power, alpha, beta, kit)
-                s.e[:nn, mm, kk] = band_lsolve(band, nn, power, power, s.e[:nn, mm, kk])
+                col[:nn, kk] = band_lsolve(band, nn, power, power, col[:nn, kk])
+        return None
+
+    _sweep_columns(s, range(min(s.e.shape[1], ci.npc)), body)
 
 
 # --------------------------------------------------------------------------- #

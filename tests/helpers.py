@@ -20,7 +20,25 @@ def oracle_kit(kit) -> mo.Kit:
 
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
     nb = np.linalg.norm(b)
-    return float(np.linalg.norm(a - b) / (nb if nb > 0 else 1.0))
+    err = float(np.linalg.norm(a - b) / (nb if nb > 0 else 1.0))
+    _log_parity(err)
+    return err
+
+
+def _log_parity(err: float):
+    """MLEGS_PARITY_LOG=<file>: append every measured relative error with the test and source line that asked for it
+    (the evidence behind the tolerances written in the tests; profiles/r2/parity_errors.jsonl)."""
+    import os
+    path = os.environ.get("MLEGS_PARITY_LOG")
+    if not path:
+        return
+    import inspect
+    import json
+    fr = inspect.stack()[2]
+    rec = {"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "where": f"{os.path.basename(fr.filename)}:{fr.lineno}",
+           "code": (fr.code_context[0].strip() if fr.code_context else ""), "rel_l2": err}
+    with open(path, "a") as fh:
+        fh.write(json.dumps(rec) + "\n")
 
 
 def random_fff(okit: mo.Kit, seed: int = 0, decay: float = 8.0) -> np.ndarray:

@@ -106,8 +106,8 @@ def test_cuda_reproduces_golden(name):
         uz = vortex.uniform_z_fld(kit)
         assert rel_l2(psi.download(), g["qvort_psi0"]) < TOL and rel_l2(chi.download(), g["qvort_chi0"]) < TOL
         st = vortex.bootstrap(kit, dt, psi, chi, uz)
-        assert rel_l2(st.psi.download(), g["boot_psi"]) < 1e-10 and rel_l2(st.chi.download(), g["boot_chi"]) < 1e-10
+        assert rel_l2(st.psi.download(), g["boot_psi"]) < TOL and rel_l2(st.chi.download(), g["boot_chi"]) < TOL
         for _ in range(2):
             vortex.step(st, dt)
-        assert rel_l2(st.psi.download(), g["step2_psi"]) < 1e-10 and rel_l2(st.chi.download(), g["step2_chi"]) < 1e-10
+        assert rel_l2(st.psi.download(), g["step2_psi"]) < TOL and rel_l2(st.chi.download(), g["step2_chi"]) < TOL
         assert abs(st.psi.ln - float(g["step2_psi_ln"])) <= 1e-10 * max(1.0, abs(float(g["step2_psi_ln"])))

@@ -17,6 +17,25 @@ CASES = {
     "hyper6": (48, 16, 12, 44, 9, 6, 3.0, 6, 1.0e-3, 1.0e-6),
 }
 TOL = 1.0e-12
+_EPS = float(np.finfo(np.float64).eps)
+
+
+def _helmp_cond(ok, power, alpha, beta):
+    """2-norm condition number of the worst (del^p + beta del^2 + alpha) system the oracle factors (ops:958-965)."""
+    worst = 1.0
+    kz = sorted({0, ok.p.nzchop - 1})
+    for mm in sorted({0, ok.p.npchop - 1}):
+        nn = ok.p.nrchop - mm
+        for kk in kz:
+            band = mo.helmp_band(int(ok.m[mm]), float(ok.ak[kk]), nn, power, alpha, beta, ok)
+            full = np.zeros((nn, nn))
+            for d, v in band.items():
+                i = np.arange(nn)
+                j = i + d
+                sel = (j >= 0) & (j < nn)
+                full[i[sel], j[sel]] = v[sel]
+            worst = max(worst, float(np.linalg.cond(full)))
+    return worst
 
 
 def _setup(case, **over):
@@ -128,7 +147,12 @@ def test_helmp_and_ihelmp(case, power):
         s, so = _pair(ok, e, "FFF", ln)
         mb.ihelmp(s, power, alpha, beta)
         mo.ihelmp(so, power, alpha, beta, ok)
-        assert rel_l2(s.download(), so.e) < 1e-10, ("ihelmp", case, power, ln)
+        # 1e-12, except where the reference's own answer is not defined that sharply: two backward-stable solves of
+        # systems whose entries differ by rounding agree to eps * cond (the oracle's band matrix of the worst (m,k)).
+        # Only (power 8, gate2d: ell = 1, m <= 24, alpha = 3e5) exceeds the bar: cond 1e9, measured 1.4e-11
+        # (profiles/r2/parity_errors.jsonl); every other case measures <= 1.2e-13.
+        assert rel_l2(s.download(), so.e) < max(TOL, _EPS * _helmp_cond(ok, power, alpha, beta)), \
+            ("ihelmp", case, power, ln)
     with pytest.raises(mb.MlegsError, match="ihelmp: alpha equals to zero"):
         mb.ihelmp(s, power, 0.0, beta)
     with pytest.raises(mb.MlegsError, match="helmp: even power greater than or equal to 4"):
@@ -145,18 +169,18 @@ def test_ihelm_and_idel2(case):
         s, so = _pair(ok, e, "FFF", ln)
         mb.ihelm(s, -200.0)
         mo.ihelm(so, -200.0, ok)
-        assert rel_l2(s.download(), so.e) < 1e-11, ("ihelm", case, ln)
+        assert rel_l2(s.download(), so.e) < TOL, ("ihelm", case, ln)
         assert abs(s.ln - so.ln) <= 1e-13 * max(1.0, abs(so.ln))
     s, so = _pair(ok, e, "FFF")
     mb.idel2(s)
     mo.idel2_proln(so, ok)
-    assert rel_l2(s.download(), so.e) < 1e-10, ("idel2_proln", case)
-    assert abs(s.ln - so.ln) <= 1e-10 * max(1.0, abs(so.ln))
+    assert rel_l2(s.download(), so.e) < TOL, ("idel2_proln", case)
+    assert abs(s.ln - so.ln) <= TOL * max(1.0, abs(so.ln))
     s, so = _pair(ok, e, "FFF")
     mb.idel2(s, preln=0.7)
     mo.idel2_preln(so, ok, 0.7)
-    assert rel_l2(s.download(), so.e) < 1e-10, ("idel2_preln", case)
-    assert abs(s.ln - so.ln) <= 1e-10 * max(1.0, abs(so.ln))
+    assert rel_l2(s.download(), so.e) < TOL, ("idel2_preln", case)
+    assert abs(s.ln - so.ln) <= TOL * max(1.0, abs(so.ln))
     with pytest.raises(mb.MlegsError, match="ihelm: alpha equals to zero"):
         mb.ihelm(s, 0.0)
 
@@ -210,7 +234,7 @@ def test_time_integrators(case):
         nl, nlo = _pair(ok, n1, "FFF", -0.05)
         getattr(mb, name)(s, nl, dt)
         getattr(mo, name)(so, nlo, dt, ok)
-        assert rel_l2(s.download(), so.e) < 1e-10, (case, name)
+        assert rel_l2(s.download(), so.e) < TOL, (case, name)
         assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
     s, so = _pair(ok, e, "FFF", 0.1)
     sp, spo = _pair(ok, e, "FFF", 0.1)
@@ -219,8 +243,8 @@ def test_time_integrators(case):
     for _ in range(2):
         mb.abcn(s, sp, nl, nlp, dt)
         mo.abcn(so, spo, nlo, nlpo, dt, ok)
-        assert rel_l2(s.download(), so.e) < 1e-10, (case, "abcn")
-        assert rel_l2(sp.download(), spo.e) < 1e-10
+        assert rel_l2(s.download(), so.e) < TOL, (case, "abcn")
+        assert rel_l2(sp.download(), spo.e) < TOL
         assert rel_l2(nlp.download(), nlpo.e) < 1e-15
         assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
     s.space = "PPP"
@@ -256,10 +280,10 @@ def test_vector_operations(case):
     p2o, c2o = mo.scalar_init(ok, "FFF"), mo.scalar_init(ok, "FFF")
     mb.vec2tp(*v, p2, c2)
     mo.vec2tp(*vo, p2o, c2o, ok)
-    assert rel_l2(p2.download(), p2o.e) < 1e-10
-    assert rel_l2(c2.download(), c2o.e) < 1e-10
-    assert abs(p2.ln - p2o.ln) <= 1e-12 * max(1.0, abs(p2o.ln))
-    assert abs(c2.ln - c2o.ln) <= 1e-10 * max(1.0, abs(c2o.ln))
+    assert rel_l2(p2.download(), p2o.e) < TOL
+    assert rel_l2(c2.download(), c2o.e) < TOL
+    assert abs(p2.ln - p2o.ln) <= TOL * max(1.0, abs(p2o.ln))
+    assert abs(c2.ln - c2o.ln) <= TOL * max(1.0, abs(c2o.ln))
 
 
 def test_qvortex_known_answer_on_device():
@@ -285,8 +309,10 @@ def test_qvortex_known_answer_on_device():
     assert np.max(np.abs(vr[:48, :4, :4])) < 1e-12
     psi2, chi2 = mb.Scalar("FFF"), mb.Scalar("FFF")
     mb.vec2tp(*out, psi2, chi2)
-    assert rel_l2(psi2.download(), psi.download()) < 1e-9
-    assert rel_l2(chi2.download(), chi.download()) < 1e-9
+    # not an oracle comparison: vec2tp(tp2vec(psi, chi)) returns to (psi, chi) up to the conditioning of the Poisson
+    # solves inside vec2tp (measured 1.6e-12 / 1.9e-11)
+    assert rel_l2(psi2.download(), psi.download()) < 1e-10
+    assert rel_l2(chi2.download(), chi.download()) < 1e-10
 
 
 def test_vortex_time_steps_gate_config():
@@ -309,9 +335,9 @@ def test_vortex_time_steps_gate_config():
     for step in range(nsteps + 1):
         ep, ec = rel_l2(st.psi.download(), sto.psi.e), rel_l2(st.chi.download(), sto.chi.e)
         errs.append((ep, ec))
-        assert ep < 1e-10 and ec < 1e-10, (step, errs)
-        assert abs(st.psi.ln - sto.psi.ln) <= 1e-10 * max(1.0, abs(sto.psi.ln))
-        assert abs(st.gain_psi - sto.gain_psi) <= 1e-9
+        assert ep < TOL and ec < TOL, (step, errs)
+        assert abs(st.psi.ln - sto.psi.ln) <= TOL * max(1.0, abs(sto.psi.ln))
+        assert abs(st.gain_psi - sto.gain_psi) <= TOL
         if step < nsteps:
             vortex.step(st, dt)
             mo.vortex_step(sto, ok, dt)
@@ -364,7 +390,7 @@ def test_on_device_initial_conditions_and_vort_mag(case):
         wro, wpo, wzo = mo.tp2curlvec(psio, chio, ok)
         want = np.sqrt(wro.e.real ** 2 + wpo.e.real ** 2 + wzo.e.real ** 2) + 1j * np.sqrt(
             wro.e.imag ** 2 + wpo.e.imag ** 2 + wzo.e.imag ** 2)
-        assert rel_l2(mag.download(), want) < 1e-10
+        assert rel_l2(mag.download(), want) < TOL
     with pytest.raises(mb.MlegsError, match="must be in PPP"):
         mb.gauss_vortices(psi, [(0.0, 0.0)])
 
@@ -415,7 +441,7 @@ def test_abab_and_helm(case, inviscid):
         for _ in range(2):
             mb.abab(s, sp, nl, nlp, dt, is_2nd_svis_p=flag)
             mo.abab(so, spo, nlo, nlpo, dt, ok, is_2nd_svis_p=flag)
-            assert rel_l2(s.download(), so.e) < 1e-10, (case, inviscid, flag)
+            assert rel_l2(s.download(), so.e) < TOL, (case, inviscid, flag)
             assert np.array_equal(sp.download(), s.download()) and np.array_equal(nlp.download(), nl.download())
             assert abs(s.ln - so.ln) <= 1e-12 * max(1.0, abs(so.ln))
     if not inviscid:

@@ -166,3 +166,34 @@ def test_qvortex_tp_roundtrip():
     mo.vec2tp(vr, vp, vz, psi2, chi2, kit)
     assert np.linalg.norm(psi2.e - psi.e) / np.linalg.norm(psi.e) < 1e-9
     assert np.linalg.norm(chi2.e - chi.e) / np.linalg.norm(chi.e) < 1e-9
+
+
+def test_forked_column_sweeps_are_bit_identical():
+    """mo.set_workers(n) runs the per-(m,k) sweeps of the band operators and solves on forked processes, one azimuthal
+    column per task; the arithmetic per column is the same code, so results must equal the serial sweep bit for bit."""
+    import mlegs_b200 as mb
+    from helpers import oracle_params, random_fff
+    p = mb.make_params(24, 12, 8, 24, 7, 5, ell=3.0, zlen=2 * np.pi, visc=1e-3, hyperpow=4, hypervisc=1e-6)
+    kit = mb.TfmKit.build_tables(p)
+    ok = mo.kit_init(oracle_params(p), tables=kit.tables())
+    e = random_fff(ok, seed=3)
+
+    def run_all():
+        out = []
+        for fn in (lambda s: mo.del2(s, ok), lambda s: mo.xxdx(s, ok), lambda s: mo.ihelm(s, -50.0, ok),
+                   lambda s: mo.ihelmp(s, 4, -1e4, 3.0, ok), lambda s: mo.idel2_proln(s, ok),
+                   lambda s: mo.idel2_preln(s, ok, 0.3)):
+            s = mo.Scalar(e=e.copy(order="F"), space="FFF", ln=0.2)
+            fn(s)
+            out.append((s.e.copy(), s.ln))
+        return out
+
+    mo.set_workers(1)
+    serial = run_all()
+    mo.set_workers(3)
+    try:
+        forked = run_all()
+    finally:
+        mo.set_workers(1)
+    for (a, la), (b, lb) in zip(serial, forked):
+        assert np.array_equal(a, b) and la == lb
