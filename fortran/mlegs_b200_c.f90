@@ -95,6 +95,12 @@ module mlegs_b200_c
       type(c_mlegs_field), intent(inout) :: s
       integer(c_int) :: rc
     end function
+    !> fftreat, ops:1002-1063
+    function mlegs_b200_fftreat(s) bind(C, name='mlegs_b200_fftreat') result(rc)
+      import :: c_mlegs_field, c_int
+      type(c_mlegs_field), intent(inout) :: s
+      integer(c_int) :: rc
+    end function
     function mlegs_b200_dealias(s) bind(C, name='mlegs_b200_dealias') result(rc)
       import :: c_mlegs_field, c_int
       type(c_mlegs_field), intent(inout) :: s

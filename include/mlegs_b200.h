@@ -81,6 +81,14 @@ int mlegs_b200_dmma_peak(double *tflops);
 int mlegs_b200_tfm_tables(const mlegs_params *p, double *x, double *w, double *ln, double *r,
                           double *lognorm, double *pf, double *at0, double *at1, double *ak);
 
+/* The same through an on-disk cache (sinit:254-300 is the reference's documented slow phase):
+ * <cache_dir>/mlegs_tables_<nr>_<nrchop>_<npchop>.bin holds x, w, lognorm, pf, at0, at1 (they depend on that triple
+ * only) with a checksum; a missing or damaged file is rebuilt and rewritten atomically.  cache_dir NULL or "" builds
+ * without caching.  *from_cache (may be NULL) reports whether the file was used. */
+int mlegs_b200_tfm_tables_cached(const mlegs_params *p, const char *cache_dir, double *x, double *w, double *ln,
+                                 double *r, double *lognorm, double *pf, double *at0, double *at1, double *ak,
+                                 int *from_cache);
+
 /* Upload the kit once; tables stay resident in HBM (replaces the host-side use of the global
  * `tfm` by ops:*).  rank/nranks describe the slab decomposition (dist:508-578 with
  * dims = (/nranks,1/)); peer buffers are attached later by mlegs_b200_dist_attach.       */
@@ -129,6 +137,9 @@ int mlegs_b200_svv_filter(mlegs_field *s, double *gain);                  /* ops
 int mlegs_b200_calcat0(const mlegs_field *s, double *out_nz_complex);     /* ops:237-272 */
 int mlegs_b200_calcat1(const mlegs_field *s, double *out_nz_complex);     /* ops:274-309 */
 int mlegs_b200_zeroat1(mlegs_field *s);                                   /* ops:311-325 */
+/* smooth the far-field values: delsqp, radial synthesis, five smoothing passes over the radial tail of every retained
+ * (m,k) line, radial analysis, idelsqp, zeroat1 */
+int mlegs_b200_fftreat(mlegs_field *s);                                   /* ops:1002-1063 */
 
 /* ---- spectral differential operators and solves -------------------------------------- */
 int mlegs_b200_delsqp(mlegs_field *s);                                    /* ops:327-366 */

@@ -51,6 +51,7 @@ _SIGS = {
     "mlegs_b200_prof_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "mlegs_b200_dmma_peak": (C.c_int, [_P(C.c_double)]),
     "mlegs_b200_tfm_tables": (C.c_int, [_P(Params)] + [C.c_void_p] * 9),
+    "mlegs_b200_tfm_tables_cached": (C.c_int, [_P(Params), C.c_char_p] + [C.c_void_p] * 9 + [_P(C.c_int)]),
     "mlegs_b200_init": (C.c_int, [_P(Params)] + [C.c_void_p] * 6 + [C.c_int, C.c_int]),
     "mlegs_b200_finalize": (C.c_int, []),
     "mlegs_b200_update_params": (C.c_int, [_P(Params)]),
@@ -75,6 +76,7 @@ _SIGS = {
     "mlegs_b200_calcat0": (C.c_int, [_P(Field), C.c_void_p]),
     "mlegs_b200_calcat1": (C.c_int, [_P(Field), C.c_void_p]),
     "mlegs_b200_zeroat1": (C.c_int, [_P(Field)]),
+    "mlegs_b200_fftreat": (C.c_int, [_P(Field)]),
     "mlegs_b200_delsqp": (C.c_int, [_P(Field)]),
     "mlegs_b200_idelsqp": (C.c_int, [_P(Field)]),
     "mlegs_b200_xxdx": (C.c_int, [_P(Field)]),

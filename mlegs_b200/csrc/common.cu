@@ -175,6 +175,13 @@ int mlegs_b200_tfm_tables(const mlegs_params *p, double *x, double *w, double *l
   return build_tfm_tables(p, x, w, ln, r, lognorm, pf, at0, at1, ak);
 }
 
+int mlegs_b200_tfm_tables_cached(const mlegs_params *p, const char *cache_dir, double *x, double *w, double *ln,
+                                 double *r, double *lognorm, double *pf, double *at0, double *at1, double *ak,
+                                 int *from_cache) {
+  MLEGS_TRY(validate_params(p));
+  return build_tfm_tables_cached(p, cache_dir, x, w, ln, r, lognorm, pf, at0, at1, ak, from_cache);
+}
+
 int mlegs_b200_init(const mlegs_params *p, const double *x, const double *w, const double *lognorm,
                     const double *pf, const double *at0, const double *at1, int rank, int nranks) {
   MLEGS_TRY(validate_params(p));

@@ -516,6 +516,93 @@ int launch_col_update(cplx *col, int n, int mode, const double *v1, const double
   return MLEGS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fftreat, ops:1002-1063: the part between the radial synthesis and the radial analysis.  Per retained (m,k) line:
+// e(:nr) *= (1-x)^2; rows ns0.. zeroed for m >= 1 (on EVERY plane, ops:1031-1035); five passes of smooth()
+// (ops:2149-2175) over the tail e(ns:nrdim); e(:nr) /= (1-x)^2.  One CTA per line; the tail lives in shared memory.
+// smooth() accumulates into each output point in a fixed order (the last point's spread, then the centres i-1, i,
+// i+1 ascending); a thread per output point adds its three contributions in that order, so results round like the
+// reference's sequential loop.
+// ---------------------------------------------------------------------------------------------
+#define FFTREAT_MAXTAIL 1024
+__global__ void __launch_bounds__(128) fftreat_tail_kernel(FftreatArgs a) {
+  __shared__ cplx buf[2][FFTREAT_MAXTAIL];
+  const int line = blockIdx.x;
+  const int j = line % a.npl, k = line / a.npl;
+  const int m = a.m0 + j;
+  if (m >= a.npc) return;
+  cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+  const bool kept = (k < a.nzc) || (k + 1 >= a.nzcu);
+  const int t0 = a.ns - 1;                 // first tail row (0-based)
+  const int ni = a.nrl - t0;
+  if (!kept) {
+    if (m >= 1)
+      for (int i = a.ns0 - 1 + threadIdx.x; i < a.nrl; i += blockDim.x) col[i] = make_double2(0.0, 0.0);
+    return;
+  }
+  for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
+    cplx v = col[i];
+    double f = 1.0;
+    if (i < a.nr) {
+      const double t = 1.0 - a.x[i];
+      f = t * t;
+      v = make_double2(v.x * f, v.y * f);
+    }
+    if (m >= 1 && i >= a.ns0 - 1) v = make_double2(0.0, 0.0);
+    if (i >= t0)
+      buf[0][i - t0] = v;
+    else
+      col[i] = make_double2(v.x / f, v.y / f);      // rows below the tail: (e * f) / f as the reference computes it
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int pass = 0; pass < 5; ++pass) {
+    const cplx *in = buf[cur];
+    cplx *out = buf[cur ^ 1];
+    for (int q = threadIdx.x; q < ni; q += blockDim.x) {
+      cplx o = make_double2(0.0, 0.0);
+      if (q == 0) o = in[0];
+      if (q >= ni - 3) {
+        const double w = (q == ni - 3) ? 0.2 : (q == ni - 2 ? 0.3 : 0.5);
+        o = make_double2(o.x + in[ni - 1].x * w, o.y + in[ni - 1].y * w);
+      }
+#pragma unroll
+      for (int d = -1; d <= 1; ++d) {
+        const int c = q + d;               // centre (0-based) contributing to point q
+        if (c < 1 || c > ni - 2) continue;
+        const double f = (1.0 + (double)(ni - (c + 1)) / ((double)ni - 1.0)) * 0.5;
+        const double w = (d == 0) ? f : (1.0 - f) / 2.0;
+        o = make_double2(o.x + in[c].x * w, o.y + in[c].y * w);
+      }
+      out[q] = o;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int q = threadIdx.x; q < ni; q += blockDim.x) {
+    const int i = t0 + q;
+    cplx v = buf[cur][q];
+    if (i < a.nr) {
+      const double t = 1.0 - a.x[i];
+      const double f = t * t;
+      v = make_double2(v.x / f, v.y / f);
+    }
+    col[i] = v;
+  }
+}
+
+int launch_fftreat_tail(const FftreatArgs &a, cudaStream_t st) {
+  if (a.nrl - (a.ns - 1) > FFTREAT_MAXTAIL) return fail(MLEGS_E_ARG, "fftreat: radial size too large");
+  if (a.nrl - (a.ns - 1) < 3) return fail(MLEGS_E_ARG, "smooth: the input length must be longer than or equal to 3.");
+  const int lines = a.npl * a.nzl;
+  if (lines <= 0) return MLEGS_OK;
+  prof_begin("fftreat_tail", st, 32.0 * (double)a.nrl * lines);
+  fftreat_tail_kernel<<<lines, 128, 0, st>>>(a);
+  prof_end(st);
+  KERNEL_CHECK();
+  return MLEGS_OK;
+}
+
 __global__ void tv_combine_kernel(TvCombineArgs a) {
   const size_t n = (size_t)a.nrl * a.npl * a.nzl;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {

@@ -148,6 +148,16 @@ int launch_rscale(cplx *e, int nrl, size_t ncols, int r0, int nr, const double *
 int launch_finite(const cplx *e, size_t n, int *flag, cudaStream_t st);
 int launch_col_update(cplx *col, int n, int mode, const double *v1, const double *v2, double s, cudaStream_t st);
 
+// fftreat's far-field treatment of the radially synthesised ('PFF') array, ops:1023-1054, one CTA per (m,k) line
+struct FftreatArgs {
+  cplx *e;
+  int nrl, npl, nzl, m0;
+  int nr, ns, ns0;                       // 1-based ns = nr*3/4, ns0 = min(ns+4, nr) of ops:1015-1016
+  int npc, nzc, nzcu;
+  const double *x;                       // Gauss-Legendre nodes
+};
+int launch_fftreat_tail(const FftreatArgs &a, cudaStream_t st);
+
 // vec2tp combination (ops:1413-1435) and tp2vec combination (ops:1488-1502)
 struct TpCombineArgs {
   cplx *dst;                             // psi or chi, rows < nn of the retained (m,k) columns only

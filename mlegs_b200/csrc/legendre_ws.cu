@@ -23,6 +23,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <vector>
+#include <cstdio>
 
 #include "dist_dev.cuh"
 
@@ -118,8 +120,20 @@ struct LegItemsB {
   unsigned int *ctr;                    // work counter, zeroed before the launch
 };
 
-__device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, BwdCtxWS *cx) {
-  const int it = (int)atomicAdd(L.ctr, 1u);
+// Static tile schedule: round j of the (heaviest-first) tile list goes to the CTAs in snake order -- CTA b takes tile
+// j G + b in even rounds and j G + (G-1-b) in odd ones -- so at any moment the grid works on G consecutive tiles (the L2
+// sharing the tile order is built for) and every CTA gets the same mix of heavy and light tiles.  A shared work counter
+// costs ~4000 cycles per fetch when 148 CTAs hit one address (B300_MICROARCH.md: L2-atom multi-CTA, n_conc 32 0.854), more
+// than the DMMA work of a 128^3 tile: the fetch latency, not the tensor pipe, set the pace (profiles/r2/README.md).
+__device__ __forceinline__ int ws_next_tile(int &round) {
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int it = round * G + ((round & 1) ? G - 1 - b : b);
+  ++round;
+  return it;
+}
+
+__device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, BwdCtxWS *cx, int &round) {
+  const int it = ws_next_tile(round);
   if (it >= L.total) {
     cx->valid = 0;
     return;
@@ -192,9 +206,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
   // The producer publishes tile jj+1 in the ring before it fills any stage of tile jj, so a consumer that has waited
   // for the stages of tile jj may read ring[jj+1]; tiles 0 and 1 are published before the start-up barrier.  A
   // consumer therefore never waits on a stage of a tile that does not exist.
+  int round = 0;                        // position in this CTA's tile schedule (used by the first producer thread)
   if (tid == WS_CONS) {
-    bwd_fetch(a, L, &S.ring[0]);
-    bwd_fetch(a, L, &S.ring[1]);
+    bwd_fetch(a, L, &S.ring[0], round);
+    bwd_fetch(a, L, &S.ring[1], round);
   }
   __syncthreads();   // barriers initialised, stages cleared, first tiles published
 
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
     int fetched = 2;
     auto ensure = [&](int j) {          // ring entries 0 .. j have been written (by the first producer thread)
       while (fetched <= j) {
-        if (tid == WS_CONS) bwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)]);
+        if (tid == WS_CONS) bwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)], round);
         ++fetched;
         asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PROD) : "memory");
       }
@@ -388,11 +403,18 @@ static_assert(sizeof(FwdStageWS) % 1024 == 0, "swizzled boxes need 1024-byte ali
 struct LegItemsF {
   int total, nkz, nfld, mlo, nrt;        // nrt = row tiles of the widest column
   unsigned int *ctr;
+  int exp;                               // kernel experiments (MLEGS_LEG_EXP): 1 no epilogue stores, 2 no DMMA, 4 no copies
+  unsigned long long *dbg;               // exp & 8: per-CTA timeline (globaltimer ns), 64 slots per CTA
 };
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
-__device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, FwdCtxWS *cx) {
+__device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, FwdCtxWS *cx, int &round) {
   for (;;) {
-    const int it = (int)atomicAdd(L.ctr, 1u);
+    const int it = ws_next_tile(round);
     if (it >= L.total) {
       cx->valid = 0;
       return;
@@ -434,6 +456,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t col_stride = (size_t)a.nrl * a.npl;
   const int NCH = (a.nrh + WSF_KC - 1) / WSF_KC;
+  unsigned long long *dbg = (L.exp & 8) ? L.dbg + (size_t)blockIdx.x * 64 : nullptr;
+  if (dbg && tid == 0) dbg[0] = gtimer();
 
   if (tid == 0) {
 #pragma unroll
@@ -457,11 +481,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       for (int n = first + lane; n < a.nrdim; n += 32) o[n] = make_double2(0.0, 0.0);
     }
   }
+  int round = 0;                        // position in this CTA's tile schedule (used by the first producer thread)
   if (tid == WS_CONS) {
-    fwd_fetch(a, L, &S.ring[0]);
-    fwd_fetch(a, L, &S.ring[1]);
+    fwd_fetch(a, L, &S.ring[0], round);
+    fwd_fetch(a, L, &S.ring[1], round);
   }
   __syncthreads();   // barriers initialised, stages cleared, first tiles published (same protocol as the backward kernel)
+  if (dbg && tid == 0) dbg[1] = gtimer();
 
   if (warp >= WS_CONS / 32) {
     // =============================== producer warps ===============================
@@ -473,7 +499,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     int fetched = 2;
     auto ensure = [&](int j) {
       while (fetched <= j) {
-        if (tid == WS_CONS) fwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)]);
+        if (tid == WS_CONS) fwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)], round);
         ++fetched;
         asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PROD) : "memory");
       }
@@ -493,6 +519,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int cnt = min(WSF_KC, a.nrh - i0);     // radial points of this stage (table columns beyond are TMA zero-fill)
         unsigned bytes = row_ok ? (unsigned)cnt * 16u : 0u;
         if (tid == WS_CONS) bytes += 2u * WSF_MT * 16u * 8u;
+        if (L.exp & 4) {
+          mbar_arrive(&S.full[s]);
+          continue;
+        }
         mbar_arrive_expect_tx(&S.full[s], bytes);
         if (tid == WS_CONS) {
           tma_box3(&B.A[0][0][0], &tmap, i0, x.n0, x.mglob, &S.full[s]);
@@ -592,10 +622,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
+      if (dbg && tid == 0 && jj < 15) dbg[2 + 4 * jj] = gtimer();
       for (int c = 0; c < NCH; ++c, ++g) {
         const int s = g % WSF_NS;
         mbar_wait(&S.full[s], (g / WSF_NS) & 1);
-        if (__double_as_longlong(lnval) != 0) {
+        if (dbg && tid == 0 && jj < 15 && c < 2) dbg[3 + 4 * jj + c] = gtimer();
+        if (L.exp & 2) {
+        } else if (__double_as_longlong(lnval) != 0) {
           if (swap) compute_n(IntK<1>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
           else compute_n(IntK<0>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
         } else {
@@ -605,6 +638,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.empty[s]);
       }
+      if (dbg && tid == 0 && jj < 15) dbg[5 + 4 * jj] = gtimer();
       // thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex per parity: rows n, n+1
       // of one z plane (32 contiguous bytes).  The table boxes carry real values beyond nn(m): those rows are zeros
       // of the truncated expansion.
@@ -614,7 +648,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int kz = kz0 + wq * 8 + nt * 4 + fk;
-          if (kz < a.nzl) {
+          if (kz < a.nzl && !((L.exp & 1) && acc[0][mt][nt][0] != 123.456)) {
             cplx *o = outp + (size_t)kz * col_stride + n;
             if (n < a.nrdim)
               o[0] = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
@@ -624,6 +658,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         }
       }
     }
+    if (dbg && tid == 0) dbg[63] = gtimer();
   }
 }
 
@@ -739,7 +774,6 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   }
   L.total = L.mcount * L.nfld * L.nit * L.nkz;
   L.ctr = g_ws_ctr;
-  CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
   const int grid = std::max(1, std::min(g_ws_sms, std::max(L.total, 1)));
   // several ranks: with an output buffer per scalar the rows are staged locally in destination order and shipped as
   // long runs (launch_slab_ship); without one they are put straight into the peers' windows
@@ -796,7 +830,15 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   L.nrt = mcount > 0 ? (nn_host(L.mlo) + WSF_MT - 1) / WSF_MT : 1;
   const int total = mcount * L.nfld * L.nkz * L.nrt;
   L.total = total;
-  CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
+  static const char *exp_env = getenv("MLEGS_LEG_EXP");
+  L.exp = exp_env ? atoi(exp_env) : 0;
+  L.dbg = nullptr;
+  static unsigned long long *d_dbg = nullptr;
+  if (L.exp & 8) {
+    if (!d_dbg) CUDA_TRY(cudaMalloc((void **)&d_dbg, 148 * 64 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_dbg, 0, 148 * 64 * sizeof(unsigned long long), st));
+    L.dbg = d_dbg;
+  }
   const int grid = std::max(1, std::min(g_ws_sms, std::max(total, 1)));
   LegArgs b = a;
   b.pf = tab;
@@ -806,6 +848,29 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   leg_forward_ws_kernel<<<grid, WS_THREADS, sizeof(FwdSmemWS), st>>>(b, L, *tm);
   prof_end(st);
   KERNEL_CHECK();
+  if (L.exp & 8) {   // dump the timeline of the last launch (CTAs 0, 73, 147) relative to the earliest start
+    static int dumped = 0;
+    if (++dumped == 40) {
+      std::vector<unsigned long long> h(148 * 64);
+      CUDA_TRY(cudaStreamSynchronize(st));
+      CUDA_TRY(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      unsigned long long t0 = ~0ull, t1 = 0;
+      for (int b2 = 0; b2 < grid; ++b2) {
+        t0 = std::min(t0, h[b2 * 64]);
+        t1 = std::max(t1, h[b2 * 64 + 63]);
+      }
+      fprintf(stderr, "leg_forward timeline: span %llu ns\n", t1 - t0);
+      for (int b2 : {0, 73, 147}) {
+        fprintf(stderr, "cta %d: start %llu prologue_done %llu end %llu\n  tiles (start, full0, full1, kdone):", b2,
+                h[b2 * 64] - t0, h[b2 * 64 + 1] - t0, h[b2 * 64 + 63] - t0);
+        for (int j = 0; j < 15; ++j)
+          if (h[b2 * 64 + 2 + 4 * j])
+            fprintf(stderr, " [%llu %llu %llu %llu]", h[b2 * 64 + 2 + 4 * j] - t0, h[b2 * 64 + 3 + 4 * j] - t0,
+                    h[b2 * 64 + 4 + 4 * j] - t0, h[b2 * 64 + 5 + 4 * j] - t0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return MLEGS_OK;
 }
 

@@ -45,6 +45,9 @@ extern long long g_launches;
 int build_tfm_tables(const mlegs_params *p, double *x, double *w, double *ln, double *r, double *lognorm,
                      double *pf, double *at0, double *at1, double *ak);
 
+int build_tfm_tables_cached(const mlegs_params *p, const char *cache_dir, double *x, double *w, double *ln, double *r,
+                            double *lognorm, double *pf, double *at0, double *at1, double *ak, int *from_cache);
+
 // ---- FFT plan: radix schedule + twiddles for one length ------------------------------------
 struct FftPlan {
   int n = 0;            // complex length of the in-smem FFT

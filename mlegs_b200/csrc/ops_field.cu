@@ -214,6 +214,41 @@ int zeroat1_impl(mlegs_field *s) {
 // ---------------------------------------------------------------------------------------------
 // diagonal operators
 // ---------------------------------------------------------------------------------------------
+int delsqp_impl(mlegs_field *s, bool inverse);
+
+// fftreat, ops:1002-1063: delsqp, radial synthesis of the FFF array ('PFF'), far-field smoothing of every retained
+// (m,k) line, radial analysis, idelsqp, zeroat1.
+int fftreat_impl(mlegs_field *s) {
+  MLEGS_TRY(ready());
+  Context &c = ctx();
+  ChopIdx ci;
+  MLEGS_TRY(chop_index(s, &ci));
+  MLEGS_TRY(require_fff(s));
+  const double ln = s->ln;
+  s->ln = 0.0;                                   // so%ln = 0 (ops:1018); restored below (ops:1058)
+  MLEGS_TRY(delsqp_impl(s, false));
+  cplx *home = (cplx *)s->e, *tmp = (cplx *)c.d_scratch[0];
+  MLEGS_TRY(stage_r(s, false, home, tmp));       // rtrans_backward on the FFF array; s->ln == 0: no log term
+  FftreatArgs a;
+  a.e = tmp;
+  a.nrl = s->loc_sz[0];
+  a.npl = s->loc_sz[1];
+  a.nzl = s->loc_sz[2];
+  a.m0 = s->loc_st[1];
+  a.nr = c.p.nr;
+  a.ns = c.p.nr * 3 / 4;
+  a.ns0 = std::min(a.ns + 4, c.p.nr);
+  a.npc = ci.npc;
+  a.nzc = ci.nzc;
+  a.nzcu = ci.nzcu;
+  a.x = c.d_x;
+  MLEGS_TRY(launch_fftreat_tail(a, strm()));
+  MLEGS_TRY(stage_r(s, true, tmp, home));        // rtrans_forward
+  MLEGS_TRY(delsqp_impl(s, true));
+  s->ln = ln;
+  return zeroat1_impl(s);
+}
+
 int delsqp_impl(mlegs_field *s, bool inverse) {
   MLEGS_TRY(ready());
   Context &c = ctx();
@@ -879,6 +914,7 @@ int mlegs_b200_calcat1(const mlegs_field *s, double *out) {
   return calcat_host(s, ctx().d_at1, out);
 }
 int mlegs_b200_zeroat1(mlegs_field *s) { return zeroat1_impl(s); }
+int mlegs_b200_fftreat(mlegs_field *s) { return fftreat_impl(s); }
 int mlegs_b200_delsqp(mlegs_field *s) { return delsqp_impl(s, false); }
 int mlegs_b200_idelsqp(mlegs_field *s) { return delsqp_impl(s, true); }
 int mlegs_b200_xxdx(mlegs_field *s) { return xxdx_impl(s); }

@@ -523,8 +523,10 @@ int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], do
 }
 
 // Batched host entry: the n host arrays are independent scalars (e.g. the three components a tp2vec caller
-// transforms back to back).  Three staging scalars and two copy streams keep PCIe busy in both directions:
-// the H2D copy of field j+1 and the D2H copy of field j-1 overlap the transform of field j.
+// transforms back to back).  The scalars are staged in GROUPS of up to MLEGS_MAXB: a group goes through
+// mlegs_b200_trans_many -- one launch per stage for the whole group and, on several ranks, ONE fused exchange and one
+// barrier per group instead of one per scalar -- while three sets of staging scalars and two copy streams keep PCIe
+// busy in both directions: the H2D copies of group g+1 and the D2H copies of group g-1 overlap the transform of group g.
 int mlegs_b200_trans_host_batch(int n, void *const *host_e, const char from[3], const char to[3], const double *ln) {
   Context &c = ctx();
   if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
@@ -533,8 +535,9 @@ int mlegs_b200_trans_host_batch(int n, void *const *host_e, const char from[3], 
   if (space_id(to) < 0) return fail(MLEGS_E_ARG, "trans: only taking PPP, PFP, FFP and FFF for spectral transformation");
   cudaStream_t st = (cudaStream_t)c.stream;
   const int NB = 3;
-  static mlegs_field f[NB];
+  static mlegs_field f[NB][MLEGS_MAXB];
   static size_t f_bytes = 0;
+  static int f_group = 0;
   static cudaStream_t s_in = nullptr, s_out = nullptr;
   static cudaEvent_t in_done[NB], comp_done[NB], out_done[NB];
   if (!s_in) {
@@ -546,33 +549,53 @@ int mlegs_b200_trans_host_batch(int n, void *const *host_e, const char from[3], 
       CUDA_TRY(cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming));
     }
   }
-  if (f_bytes != c.field_bytes) {
-    for (int b = 0; b < NB; ++b) {
-      if (f[b].e) cudaFree(f[b].e);
-      f[b].e = nullptr;
-      CUDA_TRY(cudaMalloc(&f[b].e, c.field_bytes));
-    }
+  // group size: what one exchange epoch carries, within 6 GB of staging memory, at most a third of the batch so that
+  // the three-deep pipeline has something to overlap
+  // One rank: PCIe is the bottleneck and small groups pipeline best (an eighth of the batch).  Several ranks: a group
+  // shares one exchange + barrier, so it is as large as an epoch carries while leaving three groups to overlap.
+  int group = c.nranks > 1 ? std::min({MLEGS_MAXB, dist_window_batch(), (n + NB - 1) / NB}) : std::min(MLEGS_MAXB, n / 8);
+  group = (int)std::max<size_t>(1, std::min<size_t>(std::max(group, 1), ((size_t)6 << 30) / (NB * c.field_bytes)));
+  if (f_bytes != c.field_bytes || f_group < group) {
+    CUDA_TRY(cudaStreamSynchronize(s_in));
+    CUDA_TRY(cudaStreamSynchronize(s_out));
+    for (int b = 0; b < NB; ++b)
+      for (int q = 0; q < MLEGS_MAXB; ++q) {
+        if (f[b][q].e) cudaFree(f[b][q].e);
+        f[b][q].e = nullptr;
+        if (q < group) CUDA_TRY(cudaMalloc(&f[b][q].e, c.field_bytes));
+      }
     f_bytes = c.field_bytes;
+    f_group = group;
   }
   // the copy streams start after everything already queued on the compute stream
   CUDA_TRY(cudaEventRecord(comp_done[0], st));
   CUDA_TRY(cudaStreamWaitEvent(s_in, comp_done[0], 0));
-  for (int j = 0; j < n; ++j) {
-    const int b = j % NB;
-    if (j >= NB) CUDA_TRY(cudaStreamWaitEvent(s_in, out_done[b], 0));   // staging buffer b is free again
-    field_set_layout(&f[b], space_id(from) == 0);
-    f[b].nrchop_offset = f[b].npchop_offset = f[b].nzchop_offset = 0;
-    set_space(&f[b], space_id(from));
-    f[b].ln = ln ? ln[j] : 0.0;
-    size_t ne = (size_t)f[b].loc_sz[0] * f[b].loc_sz[1] * f[b].loc_sz[2];
-    CUDA_TRY(cudaMemcpyAsync(f[b].e, host_e[j], ne * sizeof(cplx), cudaMemcpyHostToDevice, s_in));
+  int g = 0;
+  for (int j0 = 0; j0 < n; j0 += group, ++g) {
+    const int b = g % NB;
+    const int cnt = std::min(group, n - j0);
+    if (g >= NB) CUDA_TRY(cudaStreamWaitEvent(s_in, out_done[b], 0));   // staging set b is free again
+    mlegs_field *ptrs[MLEGS_MAXB];
+    for (int q = 0; q < cnt; ++q) {
+      mlegs_field &fq = f[b][q];
+      field_set_layout(&fq, space_id(from) == 0);
+      fq.nrchop_offset = fq.npchop_offset = fq.nzchop_offset = 0;
+      set_space(&fq, space_id(from));
+      fq.ln = ln ? ln[j0 + q] : 0.0;
+      const size_t ne = (size_t)fq.loc_sz[0] * fq.loc_sz[1] * fq.loc_sz[2];
+      CUDA_TRY(cudaMemcpyAsync(fq.e, host_e[j0 + q], ne * sizeof(cplx), cudaMemcpyHostToDevice, s_in));
+      ptrs[q] = &fq;
+    }
     CUDA_TRY(cudaEventRecord(in_done[b], s_in));
     CUDA_TRY(cudaStreamWaitEvent(st, in_done[b], 0));
-    MLEGS_TRY(trans_impl(&f[b], to));
+    MLEGS_TRY(trans_many_impl(cnt, ptrs, to));
     CUDA_TRY(cudaEventRecord(comp_done[b], st));
     CUDA_TRY(cudaStreamWaitEvent(s_out, comp_done[b], 0));
-    ne = (size_t)f[b].loc_sz[0] * f[b].loc_sz[1] * f[b].loc_sz[2];
-    CUDA_TRY(cudaMemcpyAsync(host_e[j], f[b].e, ne * sizeof(cplx), cudaMemcpyDeviceToHost, s_out));
+    for (int q = 0; q < cnt; ++q) {
+      mlegs_field &fq = f[b][q];
+      const size_t ne = (size_t)fq.loc_sz[0] * fq.loc_sz[1] * fq.loc_sz[2];
+      CUDA_TRY(cudaMemcpyAsync(host_e[j0 + q], fq.e, ne * sizeof(cplx), cudaMemcpyDeviceToHost, s_out));
+    }
     CUDA_TRY(cudaEventRecord(out_done[b], s_out));
   }
   CUDA_TRY(cudaStreamSynchronize(s_out));

@@ -8,6 +8,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -117,6 +120,77 @@ int build_tfm_tables(const mlegs_params *p, double *x, double *w, double *ln, do
   leg_tbl_m(&xm1, 1, p->nrchop, 0, lognorm, at0);
   leg_tbl_m(&xp1, 1, p->nrchop, 0, lognorm, at1);
   return MLEGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// On-disk cache of the expensive tables: x, w, lognorm, pf, at0, at1 depend on
+// (nr, nrchop, npchop) only -- not on ell, zlen, nz or the physics -- so one file per triple serves every run.
+// Layout: magic "MLEGSTB1" | int32 nr, nrchop, npchop, reserved | the six arrays as raw doubles | FNV-1a 64 of the
+// payload.  Written to a temporary name and renamed, so a concurrent reader never sees a partial file; a file
+// that fails any check is ignored and rebuilt.
+// ---------------------------------------------------------------------------------------------------------------
+static uint64_t fnv1a(const void *data, size_t n, uint64_t h) {   // FNV-1a over 64-bit words (n is a multiple of 8)
+  const uint64_t *p = (const uint64_t *)data;
+  for (size_t i = 0; i < n / 8; ++i) {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+int build_tfm_tables_cached(const mlegs_params *p, const char *cache_dir, double *x, double *w, double *ln, double *r,
+                            double *lognorm, double *pf, double *at0, double *at1, double *ak, int *from_cache) {
+  if (from_cache) *from_cache = 0;
+  if (!cache_dir || !cache_dir[0]) return build_tfm_tables(p, x, w, ln, r, lognorm, pf, at0, at1, ak);
+  const int nr = p->nr, nrh = nr / 2, ne = p->nrchop + 14, nm = p->npchop;
+  const std::string path = std::string(cache_dir) + "/mlegs_tables_" + std::to_string(nr) + "_" +
+                           std::to_string(p->nrchop) + "_" + std::to_string(nm) + ".bin";
+  struct Part {
+    double *ptr;
+    size_t n;
+  };
+  const Part parts[6] = {{x, (size_t)nr},   {w, (size_t)nr},           {lognorm, (size_t)ne * nm},
+                         {pf, (size_t)nrh * ne * nm}, {at0, (size_t)p->nrchop}, {at1, (size_t)p->nrchop}};
+  const char magic[8] = {'M', 'L', 'E', 'G', 'S', 'T', 'B', '1'};
+  const int32_t hdr[4] = {nr, p->nrchop, nm, 0};
+  if (FILE *fp = fopen(path.c_str(), "rb")) {
+    char m2[8];
+    int32_t h2[4];
+    bool ok = fread(m2, 1, 8, fp) == 8 && std::equal(m2, m2 + 8, magic) && fread(h2, 4, 4, fp) == 4 &&
+              std::equal(h2, h2 + 4, hdr);
+    uint64_t h = 1469598103934665603ull, stored = 0;
+    for (int q = 0; q < 6 && ok; ++q) {
+      ok = fread(parts[q].ptr, sizeof(double), parts[q].n, fp) == parts[q].n;
+      if (ok) h = fnv1a(parts[q].ptr, parts[q].n * sizeof(double), h);
+    }
+    ok = ok && fread(&stored, sizeof(stored), 1, fp) == 1 && stored == h;
+    fclose(fp);
+    if (ok) {
+      // the cheap, physics-dependent tables (sinit:120-134)
+      for (int i = 0; i < nr; ++i) {
+        ln[i] = -std::log(1.0 - x[i]);
+        r[i] = p->ell * std::sqrt((1.0 + x[i]) / (1.0 - x[i]));
+      }
+      for (int i = 0; i < p->nz; ++i) ak[i] = 2.0 * kPi / p->zlen * (double)(i - p->nz);
+      for (int i = 0; i <= p->nz / 2 && i < p->nz; ++i) ak[i] = 2.0 * kPi / p->zlen * (double)i;
+      if (from_cache) *from_cache = 1;
+      return MLEGS_OK;
+    }
+  }
+  MLEGS_TRY(build_tfm_tables(p, x, w, ln, r, lognorm, pf, at0, at1, ak));
+  const std::string tmp = path + ".tmp." + std::to_string((long long)std::hash<std::thread::id>()(std::this_thread::get_id()));
+  if (FILE *fp = fopen(tmp.c_str(), "wb")) {
+    bool ok = fwrite(magic, 1, 8, fp) == 8 && fwrite(hdr, 4, 4, fp) == 4;
+    uint64_t h = 1469598103934665603ull;
+    for (int q = 0; q < 6 && ok; ++q) {
+      ok = fwrite(parts[q].ptr, sizeof(double), parts[q].n, fp) == parts[q].n;
+      h = fnv1a(parts[q].ptr, parts[q].n * sizeof(double), h);
+    }
+    ok = ok && fwrite(&h, sizeof(h), 1, fp) == 1;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+  }
+  return MLEGS_OK;   // an unwritable cache directory is not an error: the tables are built either way
 }
 
 }  // namespace mlegs

@@ -38,6 +38,7 @@ class TfmKit:
     at0: np.ndarray
     at1: np.ndarray
     ak: np.ndarray
+    from_cache: bool = False
 
     @property
     def nrdim(self):
@@ -59,8 +60,11 @@ class TfmKit:
         return dict(x=self.x, w=self.w, lognorm=self.lognorm, pf=self.pf, at0=self.at0, at1=self.at1)
 
     @staticmethod
-    def build_tables(p: Params) -> "TfmKit":
-        """Host-only part of tfm%init(): no GPU needed."""
+    def build_tables(p: Params, cache_dir: str | None = None) -> "TfmKit":
+        """Host-only part of tfm%init(): no GPU needed.  cache_dir (default: $MLEGS_TABLE_CACHE if set) keeps the
+        (nr, nrchop, npchop)-dependent tables on disk between runs (mlegs_b200_tfm_tables_cached)."""
+        import os
+        cache_dir = cache_dir if cache_dir is not None else os.environ.get("MLEGS_TABLE_CACHE", "")
         ne = p.nrchop + 14
         x = np.zeros(p.nr)
         w = np.zeros(p.nr)
@@ -71,9 +75,15 @@ class TfmKit:
         at0 = np.zeros(p.nrchop)
         at1 = np.zeros(p.nrchop)
         ak = np.zeros(p.nz)
-        check(_lib.lib().mlegs_b200_tfm_tables(C.byref(p), _ptr(x), _ptr(w), _ptr(ln), _ptr(r), _ptr(lognorm),
-                                               _ptr(pf), _ptr(at0), _ptr(at1), _ptr(ak)))
-        return TfmKit(p, x, w, ln, r, lognorm, pf, at0, at1, ak)
+        hit = C.c_int(0)
+        if cache_dir:
+            os.makedirs(cache_dir, exist_ok=True)
+        check(_lib.lib().mlegs_b200_tfm_tables_cached(C.byref(p), cache_dir.encode(), _ptr(x), _ptr(w), _ptr(ln),
+                                                      _ptr(r), _ptr(lognorm), _ptr(pf), _ptr(at0), _ptr(at1),
+                                                      _ptr(ak), C.byref(hit)))
+        kit = TfmKit(p, x, w, ln, r, lognorm, pf, at0, at1, ak)
+        kit.from_cache = bool(hit.value)
+        return kit
 
     def upload(self, rank: int = 0, nranks: int = 1) -> "TfmKit":
         check(_lib.lib().mlegs_b200_init(C.byref(self.params), _ptr(self.x), _ptr(self.w), _ptr(self.lognorm),
@@ -81,8 +91,8 @@ class TfmKit:
         return self
 
     @staticmethod
-    def init(p: Params, rank: int = 0, nranks: int = 1) -> "TfmKit":
-        return TfmKit.build_tables(p).upload(rank, nranks)
+    def init(p: Params, rank: int = 0, nranks: int = 1, cache_dir: str | None = None) -> "TfmKit":
+        return TfmKit.build_tables(p, cache_dir).upload(rank, nranks)
 
 
 def finalize():

@@ -150,6 +150,7 @@ def _calcat(fn, s):
 def calcat0(s): return _calcat(_l().mlegs_b200_calcat0, s)
 def calcat1(s): return _calcat(_l().mlegs_b200_calcat1, s)
 def zeroat1(s): check(_l().mlegs_b200_zeroat1(C.byref(s.f)))
+def fftreat(s): check(_l().mlegs_b200_fftreat(C.byref(s.f)))
 def delsqp(s): check(_l().mlegs_b200_delsqp(C.byref(s.f)))
 def idelsqp(s): check(_l().mlegs_b200_idelsqp(C.byref(s.f)))
 def xxdx(s): check(_l().mlegs_b200_xxdx(C.byref(s.f)))

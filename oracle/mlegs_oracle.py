@@ -990,6 +990,60 @@ def ihelmp(s: Scalar, power: int, alpha: float, beta: float, kit: Kit):
     _sweep_columns(s, range(min(s.e.shape[1], ci.npc)), body)
 
 
+def smooth(a: np.ndarray) -> np.ndarray:
+    """ops:2149-2175: weighted three-point smoothing of a far-field tail, the last point spread over the last three."""
+    ni = a.size
+    if ni < 3:
+        raise ValueError("smooth: the input length must be longer than or equal to 3.")
+    out = np.zeros(ni, dtype=np.complex128)
+    out[0] = a[0]
+    out[ni - 3:ni] = out[ni - 3:ni] + a[ni - 1] * np.array([0.2, 0.3, 0.5])
+    for i in range(2, ni):               # reference i = 2 .. ni-1 (1-based): element a(i) = a[i-1]
+        f = (1.0 + (ni - i) / (ni - 1.0)) * 0.5
+        out[i - 2:i + 1] = out[i - 2:i + 1] + a[i - 1] * np.array([(1.0 - f) / 2.0, f, (1.0 - f) / 2.0])
+    return out
+
+
+def fftreat(s: Scalar, kit: Kit):
+    """Smooth the far-field values of a scalar; ops:1002-1063.  The radial synthesis acts on the FFF array directly
+    (the non-standard 'PFF' state of ops:1021), the tail rows ns.. of every retained (m,k) line are zeroed for
+    m >= 1 beyond ns0, smoothed five times (over the whole tail INCLUDING the padding rows nr..nrdim-1), and the
+    result goes back through the radial analysis."""
+    ci = chop_index(s, kit)
+    _require_fff(s, kit)
+    p = kit.p
+    nr = p.nr
+    ns = nr * 3 // 4
+    ns0 = min(ns + 4, nr)
+    so = s.copy()
+    ln = s.ln
+    so.ln = 0.0
+    delsqp(so, kit)
+    rtrans_backward(so, kit)
+    so.space = "PFF"
+    first, second = k_ranges(ci, so.e.shape[2])
+    kept = list(first) + [k for k in second if k not in set(first)]
+    ncol = min(so.e.shape[1], ci.npc)
+    fac = (1.0 - kit.x[:nr]) ** 2.0
+    for mm in range(ncol):
+        for kk in kept:
+            so.e[:nr, mm, kk] = so.e[:nr, mm, kk] * fac
+    so.e[ns0 - 1:, 1:ncol, :] = 0.0                       # loc_st(2) == 0: columns 2.. (m >= 1)
+    for mm in range(ncol):
+        for kk in kept:
+            for _ in range(5):
+                so.e[ns - 1:, mm, kk] = smooth(so.e[ns - 1:, mm, kk])
+    for mm in range(ncol):
+        for kk in kept:
+            so.e[:nr, mm, kk] = so.e[:nr, mm, kk] / fac
+    so.space = "FFF"
+    rtrans_forward(so, kit)
+    idelsqp(so, kit)
+    so.ln = ln
+    zeroat1(so, kit)
+    s.e, s.ln, s.space = so.e, so.ln, so.space
+
+
 # --------------------------------------------------------------------------- #
 # time integrators
 # --------------------------------------------------------------------------- #

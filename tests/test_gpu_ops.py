@@ -457,3 +457,22 @@ def test_abab_and_helm(case, inviscid):
             mb.ihelm(s2, alpha)
             mb.helm(s2, alpha)
             assert rel_l2(s2.download(), e) < 1e-9
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fftreat(case):
+    """SURVEY section 8f-4, last item: fftreat (ops:1002-1063) incl. smooth (ops:2149-2175) over the padded tail."""
+    kit, ok = _setup(case)
+    e = random_fff(ok, seed=41, decay=1.0)       # slowly decaying spectrum: the far field is not negligible
+    for ln in (0.0, 0.3):
+        s, so = _pair(ok, e, "FFF", ln)
+        mb.fftreat(s)
+        mo.fftreat(so, ok)
+        assert s.space == "FFF" and s.ln == so.ln == ln
+        assert rel_l2(s.download(), so.e) < TOL, (case, ln)
+    s, so = _pair(ok, e, "FFF", 0.1)
+    s.chop_offset(-2)                # (a positive radial offset would index at1 past nrchop in zeroat1, ops:318)
+    so.chop_offset(-2)
+    mb.fftreat(s)
+    mo.fftreat(so, ok)
+    assert rel_l2(s.download(), so.e) < TOL, (case, "chop offset")

@@ -197,3 +197,24 @@ def test_forked_column_sweeps_are_bit_identical():
         mo.set_workers(1)
     for (a, la), (b, lb) in zip(serial, forked):
         assert np.array_equal(a, b) and la == lb
+
+
+def test_smooth_and_fftreat_properties():
+    """smooth (ops:2149-2175) keeps the sum of a tail whose ends it does not touch, and reproduces the reference's
+    hand-computable 4-point case; fftreat (ops:1002-1063) leaves the far-field value at r -> infinity at zero."""
+    a = np.array([1.0, 2.0, 4.0, 8.0], dtype=np.complex128)
+    # i = 2: f = (1 + 2/3)/2 = 5/6 -> (1/12, 5/6, 1/12) * 2;  i = 3: f = (1 + 1/3)/2 = 2/3 -> (1/6, 2/3, 1/6) * 4;
+    # first point kept, last point spread (.2, .3, .5) over the last three
+    want = np.array([1.0 + 2.0 / 12.0, 8.0 * 0.2 + 2.0 * 5.0 / 6.0 + 4.0 / 6.0, 8.0 * 0.3 + 2.0 / 12.0 + 4.0 * 2.0 / 3.0,
+                     8.0 * 0.5 + 4.0 / 6.0])
+    assert np.allclose(mo.smooth(a), want, rtol=0, atol=1e-15)
+    assert abs(mo.smooth(a).sum() - a.sum()) < 1e-14          # every weight triple sums to one
+    import mlegs_b200 as mb
+    from helpers import oracle_params, random_fff
+    p = mb.make_params(32, 16, 8, 32, 9, 5, ell=4.0, zlen=2 * np.pi)
+    kit = mb.TfmKit.build_tables(p)
+    ok = mo.kit_init(oracle_params(p), tables=kit.tables())
+    s = mo.Scalar(e=random_fff(ok, seed=2, decay=1.0), space="FFF", ln=0.2)
+    mo.fftreat(s, ok)
+    assert s.space == "FFF" and s.ln == 0.2
+    assert np.max(np.abs(mo.calcat1(s, ok))) < 1e-12 * np.max(np.abs(s.e))

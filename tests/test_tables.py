@@ -49,3 +49,30 @@ def test_large_table_is_finite_and_orthonormal():
         gram = full.T @ (k.w[:, None] * full)
         lim = min(nn, 256 - m - 2)
         assert np.max(np.abs(gram[:lim, :lim] - np.eye(lim))) < 1e-11   # limited by the double-precision GL nodes (sinit:187)
+
+
+def test_table_cache_round_trip(tmp_path):
+    """the on-disk table cache returns bit-identical tables, recomputes the physics-dependent
+    ones (ln, r, ak) for the caller's ell / zlen / nz, and rebuilds a damaged file instead of trusting it."""
+    import mlegs_b200 as mb
+    p = mb.make_params(24, 12, 8, 22, 7, 5, ell=3.0, zlen=2 * np.pi)
+    fresh = mb.TfmKit.build_tables(p)
+    first = mb.TfmKit.build_tables(p, cache_dir=str(tmp_path))
+    assert not first.from_cache
+    files = list(tmp_path.iterdir())
+    assert [f.name for f in files] == ["mlegs_tables_24_22_7.bin"]
+    p2 = mb.make_params(24, 12, 16, 22, 7, 9, ell=1.5, zlen=4 * np.pi)      # other nz / ell / zlen: same file
+    second = mb.TfmKit.build_tables(p2, cache_dir=str(tmp_path))
+    assert second.from_cache
+    for name in ("x", "w", "lognorm", "pf", "at0", "at1"):
+        assert np.array_equal(getattr(first, name), getattr(fresh, name)), name
+        assert np.array_equal(getattr(second, name), getattr(fresh, name)), name
+    direct = mb.TfmKit.build_tables(p2)
+    for name in ("ln", "r", "ak"):
+        assert np.array_equal(getattr(second, name), getattr(direct, name)), name
+    raw = bytearray(files[0].read_bytes())
+    raw[len(raw) // 2] ^= 0x40                                              # flip one bit of the payload
+    files[0].write_bytes(bytes(raw))
+    third = mb.TfmKit.build_tables(p, cache_dir=str(tmp_path))
+    assert not third.from_cache and np.array_equal(third.pf, fresh.pf)
+    assert mb.TfmKit.build_tables(p, cache_dir=str(tmp_path)).from_cache    # rewritten
