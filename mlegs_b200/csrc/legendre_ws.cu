@@ -3,19 +3,28 @@
 // shapes the bulk copies cannot address).  Replaces rtrans_backward / rtrans_forward of
 // /root/reference/src/submodules/mlegs_scalar_ops.f90:1852-2008.
 //
-// Why this shape (profiles/r1 and tools/microbench): one DMMA-issuing warp per SM sub-partition already saturates
-// the FP64 tensor pipe (dmma_shapes.cu: 37.1 TFLOP/s with 4 warps per SM), and the LDS-fed inner loop alone reaches
-// 95 % of it (dmma_loop.cu) -- but a kernel whose warps also compute addresses, issue cp.async, wait for their own
-// loads, meet at a CTA barrier every 16 contraction steps and stage the epilogue through shared memory left the pipe
-// idle half of the time (with the DMMAs removed the remaining skeleton still took 80 % of the time).  So:
-//   * FOUR producer warps per CTA walk a dynamically fetched list of output tiles (heaviest first) and moves whole
-//     rows of the table and of the field with cp.async.bulk (the TMA unit; no per-thread address arithmetic, no
-//     register staging), up to 6 stages ahead, signalling full[stage] through the mbarrier transaction count;
-//   * 8 consumer warps wait on full[stage], run the stage's DMMAs, arrive on empty[stage], and store their
+// Why this shape (profiles/r1, profiles/r2 and tools/microbench): one DMMA-issuing warp per SM sub-partition can
+// saturate the FP64 tensor pipe in a pure DMMA stream (dmma_shapes.cu: 37.1 TFLOP/s with 4 warps per SM), but a kernel
+// whose warps also compute addresses, issue cp.async, wait for their own loads, meet at a CTA barrier every 16
+// contraction steps and stage the epilogue through shared memory left the pipe idle half of the time.  So:
+//   * producer warps walk a list of output tiles (heaviest first; a static snake schedule for short tiles, a work
+//     counter for long ones) and move whole rows of the table and of the field with cp.async.bulk / TMA tensor boxes
+//     (no per-thread address arithmetic, no register staging), signalling full[stage] through the mbarrier
+//     transaction count;
+//   * consumer (DMMA) warps wait on full[stage], run the stage's DMMAs, arrive on empty[stage], and store their
 //     accumulators straight to HBM at the end of a tile.  Every warp accumulates BOTH parities of its rows, so the
-//     parity combination f(i) = be + bo, f(nr-1-i) = be - bo happens in registers and a quarter warp stores 128
-//     contiguous bytes.  There is no CTA-wide barrier after start-up.
-// One persistent CTA per SM (grid = SM count).
+//     parity combination f(i) = be + bo, f(nr-1-i) = be - bo happens in registers.  No CTA-wide barrier after start-up,
+//     and no prologue: rows and columns that no tile computes are zero-filled by the DMMA warps next to their tiles.
+// Two tile shapes (template parameter NTC = z planes per tile):
+//   * NTC = 32: 8 DMMA + 4 producer warps, one persistent CTA per SM, deep stage ring;
+//   * NTC = 16: 4 DMMA + 2 producer warps, TWO persistent CTAs per SM (half the table reuse, but two independent
+//     pipelines per SM whose epilogues and stalls interleave); used by the synthesis of short transforms (nr <= 128).
+// What was tried and measured at 128^3 (8 scalars per launch; in-kernel globaltimer timelines, profiles/r2/README.md):
+// the r1 kernel spent 13 of 95 us in a zero-fill prologue (removed: 87 us); a work counter shared by 148 CTAs costs
+// ~2 us per fetch but was hidden behind the stage ring (static schedule: no change); forcing the two row groups of a CTA
+// to alternate on the tensor pipe made it worse (100 us: one warp per sub-partition reaches 58 % of the pipe in this
+// loop, two reach 83 %); an epilogue staged through the vacated stage slot and sent by TMA bulk stores was slower than
+// the direct stores (103 us).
 #include <cuda.h>
 
 #include <algorithm>
@@ -23,17 +32,20 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
-#include <vector>
-#include <cstdio>
 
 #include "dist_dev.cuh"
 
 namespace mlegs {
 
-#define WS_CONS 256                  // consumer threads
-#define WS_PROD 128                  // producer threads: a bulk copy is a warp-uniform instruction (UBLKCP), so the
-                                     // copies of a warp issue one after the other -- four warps issue four at a time
-#define WS_THREADS (WS_CONS + WS_PROD)
+// NTC z planes per tile -> NTC/8 column groups of DMMA warps x 2 row groups, one producer warp per 8 planes (a bulk
+// copy is a warp-uniform instruction, UBLKCP, so the copies of one warp issue one after the other)
+template <int NTC>
+struct WsCfg {
+  static constexpr int NCG = NTC / 8;          // column groups (8 z planes = 16 real columns each)
+  static constexpr int NCW = 2 * NCG;          // DMMA warps
+  static constexpr int NPW = NCG;              // producer warps
+  static constexpr int CONS = 32 * NCW, PROD = 32 * NPW, THREADS = CONS + PROD;
+};
 #define WS_RING 8                    // decoded tiles in flight
 #define WS_KC 16                     // contraction steps per stage
 
@@ -87,18 +99,17 @@ struct IntK {
 // backward (synthesis):  be(i,k) = sum_{n even} pf(i,n,m) a(n,k),  bo likewise over odd n,
 //                        f(i) = be + bo,  f(nr-1-i) = be - bo
 // ------------------------------------------------------------------------------------------------
-// Output tile = 64 rows i x 32 z planes of one column m of one scalar; a stage = 32 consecutive n (16 of each parity):
+// Output tile = 64 rows i x NTC z planes of one column m of one scalar; a stage = 32 consecutive n (16 of each parity):
 // the table rows pf(i0 .. i0+63, n, m) (512 contiguous bytes each) and the coefficient rows a(n .. n+31, kz) of the
-// tile's 32 planes (512 contiguous bytes each).
+// tile's planes (512 contiguous bytes each).
 #define WSB_MT 64
-#define WSB_NTC 32
 #define WSB_LDA (WSB_MT + 4)            // doubles per table row in shared memory   (fragment reads conflict-free)
 #define WSB_LDB (4 * WS_KC + 2)         // doubles per coefficient row               (idem)
-#define WSB_NS 6
 
+template <int NTC>
 struct BwdStageWS {
   double A[2][WS_KC][WSB_LDA];          // [parity of n][pair index][i]
-  double B[WSB_NTC][WSB_LDB];           // [kz][n (32 consecutive), (re, im) interleaved]
+  double B[NTC][WSB_LDB];               // [kz][n (32 consecutive), (re, im) interleaved]
 };
 struct BwdCtxWS {
   const double *pf;                     // table slice of this column, at row i0
@@ -107,24 +118,23 @@ struct BwdCtxWS {
   double lnval;
   int nn, i0, kz0, ml, fld, valid;
 };
+template <int NTC, int NS>
 struct BwdSmemWS {
-  BwdStageWS st[WSB_NS];
+  BwdStageWS<NTC> st[NS];
   BwdCtxWS ring[WS_RING];
-  unsigned long long full[WSB_NS], empty[WSB_NS];
+  unsigned long long full[NS], empty[NS];
 };
-static_assert(sizeof(BwdSmemWS) <= 227 * 1024, "shared memory of the backward kernel");
+static_assert(sizeof(BwdSmemWS<32, 6>) <= 227 * 1024, "shared memory of the backward kernel");
+static_assert(2 * (sizeof(BwdSmemWS<16, 4>) + 1024) <= 227 * 1024, "two backward CTAs per SM");
 static_assert((WSB_LDA * 8) % 16 == 0 && (WSB_LDB * 8) % 16 == 0, "bulk copy destinations must be 16-byte aligned");
 
 struct LegItemsB {
   int total, nkz, nfld, nit, mcount;    // tiles = mcount columns x nfld scalars x nit row tiles x nkz plane tiles
-  unsigned int *ctr;                    // work counter, zeroed before the launch
 };
 
 // Static tile schedule: round j of the (heaviest-first) tile list goes to the CTAs in snake order -- CTA b takes tile
 // j G + b in even rounds and j G + (G-1-b) in odd ones -- so at any moment the grid works on G consecutive tiles (the L2
-// sharing the tile order is built for) and every CTA gets the same mix of heavy and light tiles.  A shared work counter
-// costs ~4000 cycles per fetch when 148 CTAs hit one address (B300_MICROARCH.md: L2-atom multi-CTA, n_conc 32 0.854), more
-// than the DMMA work of a 128^3 tile: the fetch latency, not the tensor pipe, set the pace (profiles/r2/README.md).
+// sharing the tile order is built for) and every CTA gets the same mix of heavy and light tiles.
 __device__ __forceinline__ int ws_next_tile(int &round) {
   const int G = (int)gridDim.x, b = (int)blockIdx.x;
   const int it = round * G + ((round & 1) ? G - 1 - b : b);
@@ -132,6 +142,7 @@ __device__ __forceinline__ int ws_next_tile(int &round) {
   return it;
 }
 
+template <int NTC>
 __device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, BwdCtxWS *cx, int &round) {
   const int it = ws_next_tile(round);
   if (it >= L.total) {
@@ -146,7 +157,7 @@ __device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, 
   const int fld = rest % L.nfld, ml = rest / L.nfld;
   const int mglob = a.m0 + ml;
   cx->i0 = itile * WSB_MT;
-  cx->kz0 = kzt * WSB_NTC;
+  cx->kz0 = kzt * NTC;
   cx->pf = a.pf + (size_t)mglob * a.nrh * a.ne + cx->i0;
   cx->in = a.fb.in[fld] + (size_t)ml * a.nrl + (size_t)cx->kz0 * a.nrl * a.npl;
   cx->out = a.fb.out[fld] + (size_t)ml * a.nrl;
@@ -162,69 +173,61 @@ __device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, 
 // into the LOCAL output buffer in destination order (slab_stage_index); dist.cu's ship kernel then moves them as long
 // contiguous runs -- at 8 ranks the direct puts are 128-byte pieces and reach a third of the NVLink rate.
 template <int MODE>
-__global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs a, LegItemsB L, PeerTable pt) {
-  constexpr bool PUT = MODE == 1;
-  constexpr bool STAGE = MODE == 2;
+__device__ __forceinline__ void bwd_store(const LegArgs &a, const PeerTable &pt, int fld, int ml, int kz, int row,
+                                          size_t col_stride, cplx v) {
+  if (MODE == 1) {
+    int dq;
+    size_t dst;
+    slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, row, ml, kz, &dq, &dst);
+    reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off + fld * pt.fstride)[dst] = v;
+  } else if (MODE == 2) {
+    a.fb.out[fld][slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, row, ml, kz)] = v;
+  } else {
+    a.fb.out[fld][(size_t)kz * col_stride + (size_t)ml * a.nrl + row] = v;
+  }
+}
+
+template <int MODE, int NTC, int NS, int MINB>
+__global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB) leg_backward_ws_kernel(LegArgs a, LegItemsB L, PeerTable pt) {
+  using Cfg = WsCfg<NTC>;
+  constexpr int CONS = Cfg::CONS, PROD = Cfg::PROD, NCG = Cfg::NCG;
   extern __shared__ __align__(128) unsigned char smraw[];
-  BwdSmemWS &S = *reinterpret_cast<BwdSmemWS *>(smraw);
+  BwdSmemWS<NTC, NS> &S = *reinterpret_cast<BwdSmemWS<NTC, NS> *>(smraw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t col_stride = (size_t)a.nrl * a.npl;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < WSB_NS; ++s) {
-      mbar_init(&S.full[s], WS_PROD);
-      mbar_init(&S.empty[s], WS_CONS / 32);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&S.full[s], PROD);
+      mbar_init(&S.empty[s], Cfg::NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-
-  // rows no tile writes: nr .. nrdim-1 of every column (se = 0, ops:1975-1976) and whole columns with nn(m) == 0
-  {
-    const int ncol = L.nfld * a.npl * a.nzl;
-    for (int col = blockIdx.x * (WS_THREADS / 32) + warp; col < ncol; col += gridDim.x * (WS_THREADS / 32)) {
-      const int kz = col % a.nzl, rest = col / a.nzl;
-      const int ml = rest % a.npl, fld = rest / a.npl;
-      const int first = ws_nn_of_m(a.m0 + ml, a.nrc, a.npc) > 0 ? a.nr : 0;
-      for (int r = first + lane; r < a.nrdim; r += 32) {
-        if (PUT) {
-          int dq;
-          size_t dst;
-          slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, r, ml, kz, &dq,
-                         &dst);
-          reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + pt.data_off + fld * pt.fstride)[dst] =
-              make_double2(0.0, 0.0);
-        } else if (STAGE) {
-          a.fb.out[fld][slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, r, ml, kz)] =
-              make_double2(0.0, 0.0);
-        } else {
-          a.fb.out[fld][(size_t)kz * col_stride + (size_t)ml * a.nrl + r] = make_double2(0.0, 0.0);
-        }
-      }
-    }
   }
   // The producer publishes tile jj+1 in the ring before it fills any stage of tile jj, so a consumer that has waited
   // for the stages of tile jj may read ring[jj+1]; tiles 0 and 1 are published before the start-up barrier.  A
   // consumer therefore never waits on a stage of a tile that does not exist.
   int round = 0;                        // position in this CTA's tile schedule (used by the first producer thread)
-  if (tid == WS_CONS) {
-    bwd_fetch(a, L, &S.ring[0], round);
-    bwd_fetch(a, L, &S.ring[1], round);
+  if (tid == CONS) {
+    bwd_fetch<NTC>(a, L, &S.ring[0], round);
+    bwd_fetch<NTC>(a, L, &S.ring[1], round);
   }
-  __syncthreads();   // barriers initialised, stages cleared, first tiles published
+  __syncthreads();   // barriers initialised, first tiles published
 
-  if (warp >= WS_CONS / 32) {
+  if (warp >= Cfg::NCW) {
     // =============================== producer warps ===============================
-    // warp pw moves table rows 8 pw .. 8 pw + 7 (lanes 0-7) and coefficient rows 8 pw .. 8 pw + 7 (lanes 8-15) of a stage
-    const int pw = warp - WS_CONS / 32;
-    const int arow_l = (lane < 8) ? pw * 8 + lane : -1;
-    const int brow_l = (lane >= 8 && lane < 16) ? pw * 8 + lane - 8 : -1;
+    // warp pw moves table rows TR pw .. TR pw + TR-1 (lanes 0 .. TR-1) and coefficient rows 8 pw .. 8 pw + 7 (the next
+    // 8 lanes) of a stage
+    constexpr int TR = 2 * WS_KC / Cfg::NPW;
+    const int pw = warp - Cfg::NCW;
+    const int arow_l = (lane < TR) ? pw * TR + lane : -1;
+    const int brow_l = (lane >= TR && lane < TR + 8) ? pw * 8 + lane - TR : -1;
     int fetched = 2;
     auto ensure = [&](int j) {          // ring entries 0 .. j have been written (by the first producer thread)
       while (fetched <= j) {
-        if (tid == WS_CONS) bwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)], round);
+        if (tid == CONS) bwd_fetch<NTC>(a, L, &S.ring[fetched & (WS_RING - 1)], round);
         ++fetched;
-        asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PROD) : "memory");
+        asm volatile("bar.sync 1, %0;\n" ::"n"(PROD) : "memory");
       }
     };
     int g = 0;                          // stage counter over all tiles of this CTA
@@ -236,9 +239,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
       const unsigned arow = (unsigned)min(WSB_MT, a.nrh - x.i0) * 8u;       // bytes of one table row piece
       const int kz = x.kz0 + brow_l;
       for (int c = 0; c < nch; ++c, ++g) {
-        const int s = g % WSB_NS;
-        if (g >= WSB_NS) mbar_wait(&S.empty[s], ((g / WSB_NS) + 1) & 1);    // consumers are done with stage use g - NS
-        BwdStageWS &B = S.st[s];
+        const int s = g % NS;
+        if (g >= NS) mbar_wait(&S.empty[s], ((g / NS) + 1) & 1);            // consumers are done with stage use g - NS
+        BwdStageWS<NTC> &B = S.st[s];
         const int nbase = c * 2 * WS_KC;
         const int n = nbase + arow_l;                                       // this lane's table row
         const int nvalid = min(2 * WS_KC, x.nn - nbase);                    // coefficient rows present in this stage
@@ -267,119 +270,119 @@ __global__ void __launch_bounds__(WS_THREADS, 1) leg_backward_ws_kernel(LegArgs 
       }
     }
   } else {
-  // =============================== consumer warps ===============================
-  // warp (h, wq): rows i0 + 32 h .. + 31 (4 tiles of 8), real columns 16 wq .. 16 wq + 15 (2 tiles of 8), both parities
-  const int h = warp >> 2, wq = warp & 3;
-  const int fr = lane >> 2, fk = lane & 3;
-  double acc[2][4][2][2];
+    // =============================== consumer warps ===============================
+    // warp (h, wq): rows i0 + 32 h .. + 31 (4 tiles of 8), real columns 16 wq .. 16 wq + 15 (2 tiles of 8), both parities
+    const int h = warp / NCG, wq = warp % NCG;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[2][4][2][2];
 
-  int g = 0;
-  for (int jj = 0;; ++jj) {
-    const BwdCtxWS &x = S.ring[jj & (WS_RING - 1)];
-    if (!x.valid) break;
-    const int nn = x.nn, i0 = x.i0, kz0 = x.kz0, ml = x.ml;
-    cplx *outp = x.out;
-    const size_t woff = PUT ? pt.data_off + x.fld * pt.fstride : 0;   // this scalar's slab inside the peers' windows
-    const double lnval = x.lnval;
-    const int kpairs = (nn + 1) / 2;
-    const int nch = (kpairs + WS_KC - 1) / WS_KC;
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
-
-    for (int c = 0; c < nch; ++c, ++g) {
-      const int s = g % WSB_NS;
-      mbar_wait(&S.full[s], (g / WSB_NS) & 1);
-      const BwdStageWS &B = S.st[s];
-      const int ksteps = min(WS_KC / 4, (kpairs - c * WS_KC + 3) >> 2);     // pairs beyond the truncation are zeros
-#pragma unroll
-      for (int ks = 0; ks < WS_KC / 4; ++ks) {
-        if (ks >= ksteps) break;
-        const int k = ks * 4 + fk;
-        double af[2][4], bf[2][2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt) af[p][mt] = B.A[p][k][h * 32 + mt * 8 + fr];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt) bf[p][nt] = B.B[(wq * 16 + nt * 8 + fr) >> 1][2 * (2 * k + p) + (fr & 1)];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) dmma884(acc[p][mt][nt][0], acc[p][mt][nt][1], af[p][mt], bf[p][nt]);
+    // Whole columns without a retained coefficient are zeros (se = 0, ops:1975-1976); they have no tile.  Written here,
+    // while the first stages are in flight.  (The padding rows nr .. nrdim-1 of the other columns are written by the
+    // epilogue of their first row tile.)
+    {
+      const int nzero = a.npl - L.mcount;
+      const int ncol = L.nfld * nzero * a.nzl;
+      for (int col = blockIdx.x * Cfg::NCW + warp; col < ncol; col += gridDim.x * Cfg::NCW) {
+        const int kz = col % a.nzl, rest = col / a.nzl;
+        const int ml = L.mcount + rest % nzero, fld = rest / nzero;
+        for (int r = lane; r < a.nrdim; r += 32) bwd_store<MODE>(a, pt, fld, ml, kz, r, col_stride, make_double2(0.0, 0.0));
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.empty[s]);
     }
 
-    // epilogue: thread holds (re, im) of be and bo at row i = i0 + 32 h + 8 mt + lane/4, plane kz0 + 8 wq + 4 nt + lane%4
+    int g = 0;
+    for (int jj = 0;; ++jj) {
+      const BwdCtxWS &x = S.ring[jj & (WS_RING - 1)];
+      if (!x.valid) break;
+      const int nn = x.nn, i0 = x.i0, kz0 = x.kz0, ml = x.ml, fld = x.fld;
+      const double lnval = x.lnval;
+      const int kpairs = (nn + 1) / 2;
+      const int nch = (kpairs + WS_KC - 1) / WS_KC;
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const int ii = i0 + h * 32 + mt * 8 + fr;
-      double l1 = 0.0, l2 = 0.0;
-      if (__double_as_longlong(lnval) != 0 && ii < a.nrh) {   // + ln term of the m = 0 column (ops:219-221)
-        l1 = lnval * __ldg(&a.lnx[ii]);
-        l2 = lnval * __ldg(&a.lnx[a.nr - 1 - ii]);
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
+
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int s = g % NS;
+        mbar_wait(&S.full[s], (g / NS) & 1);
+        const BwdStageWS<NTC> &B = S.st[s];
+        const int ksteps = min(WS_KC / 4, (kpairs - c * WS_KC + 3) >> 2);     // pairs beyond the truncation are zeros
+#pragma unroll
+        for (int ks = 0; ks < WS_KC / 4; ++ks) {
+          if (ks >= ksteps) break;
+          const int k = ks * 4 + fk;
+          double af[2][4], bf[2][2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[p][mt] = B.A[p][k][h * 32 + mt * 8 + fr];
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) bf[p][nt] = B.B[(wq * 16 + nt * 8 + fr) >> 1][2 * (2 * k + p) + (fr & 1)];
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) dmma884(acc[p][mt][nt][0], acc[p][mt][nt][1], af[p][mt], bf[p][nt]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.empty[s]);
       }
+
+      // epilogue: thread holds (re, im) of be and bo at row i = i0 + 32 h + 8 mt + lane/4, plane kz0 + 8 wq + 4 nt + lane%4
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int kz = kz0 + wq * 8 + nt * 4 + fk;
-        if (ii < a.nrh && kz < a.nzl) {
-          const double er = acc[0][mt][nt][0], ei = acc[0][mt][nt][1];
-          const double orr = acc[1][mt][nt][0], oi = acc[1][mt][nt][1];
-          const cplx top = make_double2(er + orr + l1, ei + oi);
-          const cplx bot = make_double2(er - orr + l2, ei - oi);
-          if (PUT) {
-            int dq;
-            size_t dst;
-            slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, ii, ml, kz, &dq,
-                           &dst);
-            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + woff)[dst] = top;
-            slab_put_index(1, pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, pt.m_off, a.nrdim, a.npdim, a.nr - 1 - ii,
-                           ml, kz, &dq, &dst);
-            reinterpret_cast<cplx *>(reinterpret_cast<char *>(pt.base[dq]) + woff)[dst] = bot;
-          } else if (STAGE) {
-            cplx *base = outp - (size_t)ml * a.nrl;   // start of this scalar's staging buffer
-            base[slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, ii, ml, kz)] = top;
-            base[slab_stage_index(pt.rank, pt.nranks, pt.r_cnt, pt.r_off, pt.m_cnt, a.nzl, a.nr - 1 - ii, ml, kz)] = bot;
-          } else {
-            outp[(size_t)kz * col_stride + ii] = top;
-            outp[(size_t)kz * col_stride + (a.nr - 1 - ii)] = bot;
+      for (int mt = 0; mt < 4; ++mt) {
+        const int ii = i0 + h * 32 + mt * 8 + fr;
+        double l1 = 0.0, l2 = 0.0;
+        if (__double_as_longlong(lnval) != 0 && ii < a.nrh) {   // + ln term of the m = 0 column (ops:219-221)
+          l1 = lnval * __ldg(&a.lnx[ii]);
+          l2 = lnval * __ldg(&a.lnx[a.nr - 1 - ii]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int kz = kz0 + wq * 8 + nt * 4 + fk;
+          if (ii < a.nrh && kz < a.nzl) {
+            const double er = acc[0][mt][nt][0], ei = acc[0][mt][nt][1];
+            const double orr = acc[1][mt][nt][0], oi = acc[1][mt][nt][1];
+            bwd_store<MODE>(a, pt, fld, ml, kz, ii, col_stride, make_double2(er + orr + l1, ei + oi));
+            bwd_store<MODE>(a, pt, fld, ml, kz, a.nr - 1 - ii, col_stride, make_double2(er - orr + l2, ei - oi));
           }
         }
       }
+      // first row tile of its column: the padding rows nr .. nrdim-1 are zeros (se = 0, ops:1975-1976)
+      if (i0 == 0) {
+        const int kz = kz0 + wq * 8 + (lane >> 2);
+        if (kz < a.nzl)
+          for (int r = a.nr + 4 * h + (lane & 3); r < a.nrdim; r += 8)
+            bwd_store<MODE>(a, pt, fld, ml, kz, r, col_stride, make_double2(0.0, 0.0));
+      }
     }
-  }
   }   // consumers
-  if (PUT) dist_finish_put(pt, gridDim.x);
+  if (MODE == 1) dist_finish_put(pt, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward (analysis):  a(n,k) = sum_{i<nr/2} [pf(i,n,m) w(i)] * (f(i,k) + (-1)^n f(nr-1-i,k))
 // ------------------------------------------------------------------------------------------------
-// Output tile = 128 consecutive n (64 of each parity) x 32 z planes of one column m of one scalar; a stage = 32
+// Output tile = 128 consecutive n (64 of each parity) x NTC z planes of one column m of one scalar; a stage = 32
 // radial points i.  The table slice arrives as two TMA tensor boxes (16 i x 128 n, 128-byte swizzle: fragment reads are
 // bank-conflict free without padding); the field rows f(i0.., kz) and their mirrors f(.. nr-1-i0, kz) arrive as 512-byte
 // bulk copies.  The quadrature weight is folded into the table once at start-up (pf*w, resident in HBM), so the parity
 // fold left in the DMMA warps' fragment path is one DADD per B fragment: (top + mirror) feeds the rows of one
 // parity, (top - mirror) the other.
 #define WSF_MT 128
-#define WSF_NTC 32
 #define WSF_KC 32                        // radial points per stage
 #define WSF_LDK (WSF_KC + 4)             // complex elements per field row in shared memory (fragment reads conflict-free)
-#define WSF_NS 3
 
+template <int NTC>
 struct FwdStageWS {
   double A[2][WSF_MT][16];               // two swizzled TMA boxes: [k / 16][n][k % 16, 16-byte chunks XOR (n & 7)]
-  double T[WSF_NTC][2 * WSF_LDK];        // f(i0 + k, kz), (re, im) interleaved
-  double Bm[WSF_NTC][2 * WSF_LDK];       // f(nr-1-i0-k, kz) at complex index WSF_KC-1-k
+  double T[NTC][2 * WSF_LDK];            // f(i0 + k, kz), (re, im) interleaved
+  double Bm[NTC][2 * WSF_LDK];           // f(nr-1-i0-k, kz) at complex index WSF_KC-1-k
 };
 struct FwdCtxWS {
   const cplx *in;                        // f(0, m, kz0)
@@ -387,13 +390,16 @@ struct FwdCtxWS {
   double lnval;
   int nn, n0, kz0, mglob, valid;
 };
+template <int NTC, int NS>
 struct FwdSmemWS {
-  FwdStageWS st[WSF_NS];
+  FwdStageWS<NTC> st[NS];
   FwdCtxWS ring[WS_RING];
-  unsigned long long full[WSF_NS], empty[WSF_NS];
+  unsigned long long full[NS], empty[NS];
 };
-static_assert(sizeof(FwdSmemWS) <= 227 * 1024, "shared memory of the forward kernel");
-static_assert(sizeof(FwdStageWS) % 1024 == 0, "swizzled boxes need 1024-byte alignment");
+static_assert(sizeof(FwdSmemWS<32, 3>) <= 227 * 1024, "shared memory of the forward kernel");
+static_assert(2 * (sizeof(FwdSmemWS<16, 2>) + 1024) <= 227 * 1024, "two forward CTAs per SM");
+static_assert(sizeof(FwdStageWS<32>) % 1024 == 0 && sizeof(FwdStageWS<16>) % 1024 == 0,
+              "swizzled boxes need 1024-byte alignment");
 
 // Tile order: row tile fastest, then z tile, then scalar, then column m (heaviest columns first).  The row tiles of one
 // (m, scalar, z tile) read the same field rows and run at the same time on neighbouring SMs, so the field is fetched
@@ -402,19 +408,17 @@ static_assert(sizeof(FwdStageWS) % 1024 == 0, "swizzled boxes need 1024-byte ali
 // same few hundred tiles.  Row tiles beyond the truncation of their column are skipped at fetch time.
 struct LegItemsF {
   int total, nkz, nfld, mlo, nrt;        // nrt = row tiles of the widest column
-  unsigned int *ctr;
-  int exp;                               // kernel experiments (MLEGS_LEG_EXP): 1 no epilogue stores, 2 no DMMA, 4 no copies
-  unsigned long long *dbg;               // exp & 8: per-CTA timeline (globaltimer ns), 64 slots per CTA
+  int mcount;                            // columns [mlo, mlo + mcount) have retained rows
+  unsigned int *ctr;                     // != nullptr: tiles are claimed from this counter instead of the static schedule
 };
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
+template <int NTC>
 __device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, FwdCtxWS *cx, int &round) {
   for (;;) {
-    const int it = ws_next_tile(round);
+    // Long tiles (nr >= 512: 8+ stages each) are claimed from a counter: the row tiles of one (m, z tile) then run at
+    // the same time and share their field rows in L2 (a static schedule drifts apart: 512^3 forward 3.5 -> 4.1 ms).
+    // Short tiles use the static schedule: a fetch from a counter every CTA hits costs more than their DMMA work.
+    const int it = L.ctr ? (int)atomicAdd(L.ctr, 1u) : ws_next_tile(round);
     if (it >= L.total) {
       cx->valid = 0;
       return;
@@ -426,8 +430,8 @@ __device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, 
     const int fld = rest % L.nfld, ml = L.mlo + rest / L.nfld;
     const int mglob = a.m0 + ml;
     const int nn = ws_nn_of_m(mglob, a.nrc, a.npc);
-    if (r * WSF_MT >= nn) continue;      // nothing retained in this row tile: the zero-fill pass covers it
-    cx->kz0 = kzt * WSF_NTC;
+    if (r * WSF_MT >= nn) continue;      // nothing retained in this row tile: the last row tile with work zero-fills it
+    cx->kz0 = kzt * NTC;
     cx->in = a.fb.in[fld] + (size_t)ml * a.nrl + (size_t)cx->kz0 * a.nrl * a.npl;
     cx->out = a.fb.out[fld] + (size_t)ml * a.nrl;
     cx->lnval = (mglob == 0) ? a.fb.ln[fld] : 0.0;
@@ -448,60 +452,46 @@ __device__ __forceinline__ void tma_box3(void *dst, const CUtensorMap *tm, int c
       : "memory");
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 1)
+template <int NTC, int NS, int MINB>
+__global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
     leg_forward_ws_kernel(LegArgs a, LegItemsF L, const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = WsCfg<NTC>;
+  constexpr int CONS = Cfg::CONS, PROD = Cfg::PROD, NCG = Cfg::NCG;
   extern __shared__ __align__(1024) unsigned char smraw_f[];
-  FwdSmemWS &S = *reinterpret_cast<FwdSmemWS *>(smraw_f);   // no static shared memory: the window starts 1024-aligned
-  if ((smem_u32(smraw_f) & 1023u) != 0) __trap();           // the swizzled boxes rely on it
+  FwdSmemWS<NTC, NS> &S = *reinterpret_cast<FwdSmemWS<NTC, NS> *>(smraw_f);   // no static shared memory: 1024-aligned
+  if ((smem_u32(smraw_f) & 1023u) != 0) __trap();                              // the swizzled boxes rely on it
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t col_stride = (size_t)a.nrl * a.npl;
   const int NCH = (a.nrh + WSF_KC - 1) / WSF_KC;
-  unsigned long long *dbg = (L.exp & 8) ? L.dbg + (size_t)blockIdx.x * 64 : nullptr;
-  if (dbg && tid == 0) dbg[0] = gtimer();
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < WSF_NS; ++s) {
-      mbar_init(&S.full[s], WS_PROD);
-      mbar_init(&S.empty[s], WS_CONS / 32);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&S.full[s], PROD);
+      mbar_init(&S.empty[s], Cfg::NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-
-  // rows that no tile writes are zeros (se = 0, ops:1898-1899): [ceil128(nn(m)), nrdim) of every column
-  {
-    const int ncol = L.nfld * a.npl * a.nzl;
-    for (int col = blockIdx.x * (WS_THREADS / 32) + warp; col < ncol; col += gridDim.x * (WS_THREADS / 32)) {
-      const int kz = col % a.nzl, rest = col / a.nzl;
-      const int ml = rest % a.npl, fld = rest / a.npl;
-      const int mglob = a.m0 + ml;
-      const int nn = (a.skip_m0 && mglob == 0) ? 0 : ws_nn_of_m(mglob, a.nrc, a.npc);
-      const int first = min(a.nrdim, (nn + WSF_MT - 1) / WSF_MT * WSF_MT);
-      cplx *o = a.fb.out[fld] + (size_t)kz * col_stride + (size_t)ml * a.nrl;
-      for (int n = first + lane; n < a.nrdim; n += 32) o[n] = make_double2(0.0, 0.0);
-    }
-  }
   int round = 0;                        // position in this CTA's tile schedule (used by the first producer thread)
-  if (tid == WS_CONS) {
-    fwd_fetch(a, L, &S.ring[0], round);
-    fwd_fetch(a, L, &S.ring[1], round);
+  if (tid == CONS) {
+    fwd_fetch<NTC>(a, L, &S.ring[0], round);
+    fwd_fetch<NTC>(a, L, &S.ring[1], round);
   }
-  __syncthreads();   // barriers initialised, stages cleared, first tiles published (same protocol as the backward kernel)
-  if (dbg && tid == 0) dbg[1] = gtimer();
+  __syncthreads();   // barriers initialised, first tiles published (same protocol as the backward kernel)
 
-  if (warp >= WS_CONS / 32) {
+  if (warp >= Cfg::NCW) {
     // =============================== producer warps ===============================
     // warp pw: field rows (z planes) 8 pw .. 8 pw + 7: lanes 0-7 the top rows, lanes 8-15 the mirror rows; the first
     // producer thread also issues the two table boxes
-    const int pw = warp - WS_CONS / 32;
+    const int pw = warp - Cfg::NCW;
     const int row_l = pw * 8 + (lane & 7);
     const bool is_top = lane < 8, is_mir = lane >= 8 && lane < 16;
     int fetched = 2;
     auto ensure = [&](int j) {
       while (fetched <= j) {
-        if (tid == WS_CONS) fwd_fetch(a, L, &S.ring[fetched & (WS_RING - 1)], round);
+        if (tid == CONS) fwd_fetch<NTC>(a, L, &S.ring[fetched & (WS_RING - 1)], round);
         ++fetched;
-        asm volatile("bar.sync 1, %0;\n" ::"n"(WS_PROD) : "memory");
+        asm volatile("bar.sync 1, %0;\n" ::"n"(PROD) : "memory");
       }
     };
     int g = 0;
@@ -512,19 +502,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       const bool row_ok = (is_top || is_mir) && (x.kz0 + row_l < a.nzl);
       const cplx *src_col = x.in + (size_t)row_l * col_stride;
       for (int c = 0; c < NCH; ++c, ++g) {
-        const int s = g % WSF_NS;
-        if (g >= WSF_NS) mbar_wait(&S.empty[s], ((g / WSF_NS) + 1) & 1);
-        FwdStageWS &B = S.st[s];
+        const int s = g % NS;
+        if (g >= NS) mbar_wait(&S.empty[s], ((g / NS) + 1) & 1);
+        FwdStageWS<NTC> &B = S.st[s];
         const int i0 = c * WSF_KC;
         const int cnt = min(WSF_KC, a.nrh - i0);     // radial points of this stage (table columns beyond are TMA zero-fill)
         unsigned bytes = row_ok ? (unsigned)cnt * 16u : 0u;
-        if (tid == WS_CONS) bytes += 2u * WSF_MT * 16u * 8u;
-        if (L.exp & 4) {
-          mbar_arrive(&S.full[s]);
-          continue;
-        }
+        if (tid == CONS) bytes += 2u * WSF_MT * 16u * 8u;
         mbar_arrive_expect_tx(&S.full[s], bytes);
-        if (tid == WS_CONS) {
+        if (tid == CONS) {
           tma_box3(&B.A[0][0][0], &tmap, i0, x.n0, x.mglob, &S.full[s]);
           tma_box3(&B.A[1][0][0], &tmap, i0 + 16, x.n0, x.mglob, &S.full[s]);
         }
@@ -544,14 +530,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   } else {
     // =============================== consumer warps ===============================
     // warp (h, wq): row tiles t = 2 mt + h (8 rows of each parity = 16 consecutive n), real columns 16 wq .. 16 wq + 15
-    const int h = warp >> 2, wq = warp & 3;
+    const int h = warp / NCG, wq = warp % NCG;
     const int fr = lane >> 2, fk = lane & 3;
     const int swap = a.swap_parity;   // 0: even rows contract with the sum fold (eomul), 1: with the difference (oemul)
     double acc[2][4][2][2];
 
+    // Columns without a retained row have no tile: they are zeros (se = 0, ops:1898-1899).  Written here, by the DMMA
+    // warps, while the first stages are in flight.  (Rows beyond the last row tile of a column WITH retained rows
+    // are zeroed by that tile's epilogue.)
+    {
+      const int nzero = a.npl - L.mcount;           // columns [0, mlo) and [mlo + mcount, npl)
+      const int ncol = L.nfld * nzero * a.nzl;
+      for (int col = blockIdx.x * Cfg::NCW + warp; col < ncol; col += gridDim.x * Cfg::NCW) {
+        const int kz = col % a.nzl, rest = col / a.nzl;
+        const int zc = rest % nzero, fld = rest / nzero;
+        const int ml = zc < L.mlo ? zc : zc + L.mcount;
+        cplx *o = a.fb.out[fld] + (size_t)kz * col_stride + (size_t)ml * a.nrl;
+        for (int n = lane; n < a.nrdim; n += 32) o[n] = make_double2(0.0, 0.0);
+      }
+    }
+
     // NACT: active row tiles of this warp; SWAP: 0 = even rows contract with the sum fold (eomul), 1 = with the
     // difference (oemul); LN: remove the log term from the real part of the m = 0 column (ops:193-195)
-    auto compute = [&](auto nact_c, auto swap_c, auto ln_c, const FwdStageWS &B, int i0, double lnval) {
+    auto compute = [&](auto nact_c, auto swap_c, auto ln_c, const FwdStageWS<NTC> &B, int i0, double lnval) {
       constexpr int NACT = decltype(nact_c)::value;
       constexpr int SWAP = decltype(swap_c)::value;
       constexpr bool LN = decltype(ln_c)::value != 0;
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             }
       }
     };
-    auto compute_n = [&](auto swap_c, auto ln_c, int nact, const FwdStageWS &B, int i0, double lnval) {
+    auto compute_n = [&](auto swap_c, auto ln_c, int nact, const FwdStageWS<NTC> &B, int i0, double lnval) {
       switch (nact) {
         case 4: compute(IntK<4>{}, swap_c, ln_c, B, i0, lnval); break;
         case 3: compute(IntK<3>{}, swap_c, ln_c, B, i0, lnval); break;
@@ -622,13 +623,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
-      if (dbg && tid == 0 && jj < 15) dbg[2 + 4 * jj] = gtimer();
       for (int c = 0; c < NCH; ++c, ++g) {
-        const int s = g % WSF_NS;
-        mbar_wait(&S.full[s], (g / WSF_NS) & 1);
-        if (dbg && tid == 0 && jj < 15 && c < 2) dbg[3 + 4 * jj + c] = gtimer();
-        if (L.exp & 2) {
-        } else if (__double_as_longlong(lnval) != 0) {
+        const int s = g % NS;
+        mbar_wait(&S.full[s], (g / NS) & 1);
+        if (__double_as_longlong(lnval) != 0) {
           if (swap) compute_n(IntK<1>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
           else compute_n(IntK<0>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
         } else {
@@ -638,7 +636,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.empty[s]);
       }
-      if (dbg && tid == 0 && jj < 15) dbg[5 + 4 * jj] = gtimer();
       // thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex per parity: rows n, n+1
       // of one z plane (32 contiguous bytes).  The table boxes carry real values beyond nn(m): those rows are zeros
       // of the truncated expansion.
@@ -648,7 +645,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int kz = kz0 + wq * 8 + nt * 4 + fk;
-          if (kz < a.nzl && !((L.exp & 1) && acc[0][mt][nt][0] != 123.456)) {
+          if (kz < a.nzl) {
             cplx *o = outp + (size_t)kz * col_stride + n;
             if (n < a.nrdim)
               o[0] = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
@@ -657,37 +654,63 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
           }
         }
       }
+      // last row tile of its column: the rows beyond it are zeros (nr .. nrdim-1 when nrchop = nr)
+      if (n0 + WSF_MT >= nn && n0 + WSF_MT < a.nrdim) {
+        const int kz = kz0 + wq * 8 + (lane >> 2);
+        if (kz < a.nzl) {
+          cplx *o = outp + (size_t)kz * col_stride;
+          for (int n = n0 + WSF_MT + 4 * h + (lane & 3); n < a.nrdim; n += 8) o[n] = make_double2(0.0, 0.0);
+        }
+      }
     }
-    if (dbg && tid == 0) dbg[63] = gtimer();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static unsigned int *g_ws_ctr = nullptr;
 static int g_ws_sms = 0;
+static unsigned int *g_ws_ctr = nullptr;
 static std::map<const double *, CUtensorMap> g_tmaps;   // one tensor map per analysis table of the current kit
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// big shape: 32 planes per tile, one CTA per SM; small shape: 16 planes per tile, two CTAs per SM
+#define WSB_BIG 32, 6, 1
+#define WSB_SMALL 16, 4, 2
+#define WSF_BIG 32, 3, 1
+#define WSF_SMALL 16, 2, 2
+
 static int ws_setup() {
-  if (g_ws_ctr) return MLEGS_OK;
+  if (g_ws_sms) return MLEGS_OK;
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&g_ws_sms, cudaDevAttrMultiProcessorCount, dev));
-  CUDA_TRY(cudaMalloc((void **)&g_ws_ctr, 4 * sizeof(unsigned int)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(BwdSmemWS)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(BwdSmemWS)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(BwdSmemWS)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(FwdSmemWS)));
+  CUDA_TRY(cudaMalloc((void **)&g_ws_ctr, sizeof(unsigned int)));
+  const int big_b = (int)sizeof(BwdSmemWS<32, 6>), small_b = (int)sizeof(BwdSmemWS<16, 4>);
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<0, WSB_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_b));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<1, WSB_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_b));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<2, WSB_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_b));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<0, WSB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_b));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<1, WSB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_b));
+  CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<2, WSB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_b));
+  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel<WSF_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(FwdSmemWS<32, 3>)));
+  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel<WSF_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(FwdSmemWS<16, 2>)));
   return MLEGS_OK;
+}
+
+// Tile shape of a launch; MLEGS_LEG_SHAPE=big|small forces one for A/B timing.
+static bool ws_small_shape(const LegArgs &a, bool forward) {
+  static const char *force = getenv("MLEGS_LEG_SHAPE");
+  if (force) return force[0] == 's';
+  // measured (tools/leg_bench.py, profiles/r2): synthesis 128^3 75.8 us small / 77.1 big, 256^3 905 / 876; analysis
+  // 128^3 92.5 / 87.2 (the small shape re-reads the table slice twice as often and the analysis is bound by its
+  // L2 -> shared-memory fills), 256^3 1023 / 989
+  return !forward && a.nrh <= 64;
 }
 
 // table(i, n, m), i fastest: boxes of 16 i x 128 n x 1 m, 128-byte swizzle, zero fill outside the table
@@ -758,11 +781,25 @@ void leg_alg_work(const LegArgs &a, double *bytes, double *flops) {
   *bytes = nf * (16.0 * a.nr * cols * a.nzl + 16.0 * S * a.nzl);
 }
 
+template <int NTC, int NS, int MINB>
+static void launch_bwd_shape(int mode, int grid, const LegArgs &a, const LegItemsB &L, const PeerTable &pt, cudaStream_t st) {
+  const size_t smem = sizeof(BwdSmemWS<NTC, NS>);
+  const int threads = WsCfg<NTC>::THREADS;
+  if (mode == 2)
+    leg_backward_ws_kernel<2, NTC, NS, MINB><<<grid, threads, smem, st>>>(a, L, pt);
+  else if (mode == 1)
+    leg_backward_ws_kernel<1, NTC, NS, MINB><<<grid, threads, smem, st>>>(a, L, pt);
+  else
+    leg_backward_ws_kernel<0, NTC, NS, MINB><<<grid, threads, smem, st>>>(a, L, pt);
+}
+
 // `a` has its batch filled in (legendre.cu: with_batch)
 int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   MLEGS_TRY(ws_setup());
+  const bool small = ws_small_shape(a, false);
+  const int ntc = small ? 16 : 32;
   LegItemsB L;
-  L.nkz = (a.nzl + WSB_NTC - 1) / WSB_NTC;
+  L.nkz = (a.nzl + ntc - 1) / ntc;
   L.nit = (a.nrh + WSB_MT - 1) / WSB_MT;
   L.nfld = a.fb.n;
   L.mcount = 0;
@@ -773,8 +810,8 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
     ++L.mcount;
   }
   L.total = L.mcount * L.nfld * L.nit * L.nkz;
-  L.ctr = g_ws_ctr;
-  const int grid = std::max(1, std::min(g_ws_sms, std::max(L.total, 1)));
+  // even without a tile the grid covers the zero-filled columns
+  const int grid = std::max(1, std::min(g_ws_sms * (small ? 2 : 1), std::max(L.total, a.npl > L.mcount ? g_ws_sms : 1)));
   // several ranks: with an output buffer per scalar the rows are staged locally in destination order and shipped as
   // long runs (launch_slab_ship); without one they are put straight into the peers' windows
   // (2 ranks, 128^3 per rank: direct puts 192 us, staged 120 + 133 us; 8 ranks: the direct puts are 256-byte runs of
@@ -785,15 +822,14 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   double wb = 0.0, wf = 0.0;
   leg_alg_work(a, &wb, &wf);
   prof_begin(a.peer ? (stage ? "legendre_backward_stage" : "legendre_backward_put") : "legendre_backward", st, wb, wf);
-  if (stage) {
-    leg_backward_ws_kernel<2><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
-  } else if (a.peer) {
-    leg_backward_ws_kernel<1><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, *a.peer);
-  } else {
-    PeerTable none;
-    memset(&none, 0, sizeof(none));
-    leg_backward_ws_kernel<0><<<grid, WS_THREADS, sizeof(BwdSmemWS), st>>>(a, L, none);
-  }
+  PeerTable none;
+  memset(&none, 0, sizeof(none));
+  const PeerTable &pt = a.peer ? *a.peer : none;
+  const int mode = stage ? 2 : (a.peer ? 1 : 0);
+  if (small)
+    launch_bwd_shape<WSB_SMALL>(mode, grid, a, L, pt, st);
+  else
+    launch_bwd_shape<WSB_BIG>(mode, grid, a, L, pt, st);
   prof_end(st);
   KERNEL_CHECK();
   if (stage) MLEGS_TRY(launch_slab_ship(*a.peer, a.fb, st));
@@ -814,13 +850,14 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   const double *tab = a.w ? c.d_pfw : a.pf;
   const CUtensorMap *tm = nullptr;
   MLEGS_TRY(table_tmap(tab, a.nrh, a.ne, c.p.npchop, &tm));
+  const bool small = ws_small_shape(a, true);
+  const int ntc = small ? 16 : 32;
   // tiles: (column with nn(m) > 0) x scalar x z tile x row tile of the widest column; nn(m) is non-increasing in m,
   // so the columns with work form a prefix
   LegItemsF L;
-  L.nkz = (a.nzl + WSF_NTC - 1) / WSF_NTC;
+  L.nkz = (a.nzl + ntc - 1) / ntc;
   L.nfld = a.fb.n;
   L.mlo = (a.skip_m0 && a.m0 == 0) ? 1 : 0;
-  L.ctr = g_ws_ctr;
   auto nn_host = [&](int ml) {
     const int m = a.m0 + ml;
     return m < a.npc ? std::min(std::max(std::min(a.nrc, a.nrc - m), 0), a.nrdim) : 0;
@@ -830,47 +867,25 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   L.nrt = mcount > 0 ? (nn_host(L.mlo) + WSF_MT - 1) / WSF_MT : 1;
   const int total = mcount * L.nfld * L.nkz * L.nrt;
   L.total = total;
-  static const char *exp_env = getenv("MLEGS_LEG_EXP");
-  L.exp = exp_env ? atoi(exp_env) : 0;
-  L.dbg = nullptr;
-  static unsigned long long *d_dbg = nullptr;
-  if (L.exp & 8) {
-    if (!d_dbg) CUDA_TRY(cudaMalloc((void **)&d_dbg, 148 * 64 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(d_dbg, 0, 148 * 64 * sizeof(unsigned long long), st));
-    L.dbg = d_dbg;
+  L.mcount = mcount;
+  L.ctr = nullptr;
+  if (!small && (a.nrh + WSF_KC - 1) / WSF_KC >= 8) {
+    L.ctr = g_ws_ctr;
+    CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
   }
-  const int grid = std::max(1, std::min(g_ws_sms, std::max(total, 1)));
+  // even without a tile the grid covers the zero-filled columns
+  const int grid = std::max(1, std::min(g_ws_sms * (small ? 2 : 1), std::max(total, a.npl > mcount ? g_ws_sms : 1)));
   LegArgs b = a;
   b.pf = tab;
   double wb = 0.0, wf = 0.0;
   leg_alg_work(a, &wb, &wf);
   prof_begin("legendre_forward", st, wb, wf);
-  leg_forward_ws_kernel<<<grid, WS_THREADS, sizeof(FwdSmemWS), st>>>(b, L, *tm);
+  if (small)
+    leg_forward_ws_kernel<WSF_SMALL><<<grid, WsCfg<16>::THREADS, sizeof(FwdSmemWS<16, 2>), st>>>(b, L, *tm);
+  else
+    leg_forward_ws_kernel<WSF_BIG><<<grid, WsCfg<32>::THREADS, sizeof(FwdSmemWS<32, 3>), st>>>(b, L, *tm);
   prof_end(st);
   KERNEL_CHECK();
-  if (L.exp & 8) {   // dump the timeline of the last launch (CTAs 0, 73, 147) relative to the earliest start
-    static int dumped = 0;
-    if (++dumped == 40) {
-      std::vector<unsigned long long> h(148 * 64);
-      CUDA_TRY(cudaStreamSynchronize(st));
-      CUDA_TRY(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      unsigned long long t0 = ~0ull, t1 = 0;
-      for (int b2 = 0; b2 < grid; ++b2) {
-        t0 = std::min(t0, h[b2 * 64]);
-        t1 = std::max(t1, h[b2 * 64 + 63]);
-      }
-      fprintf(stderr, "leg_forward timeline: span %llu ns\n", t1 - t0);
-      for (int b2 : {0, 73, 147}) {
-        fprintf(stderr, "cta %d: start %llu prologue_done %llu end %llu\n  tiles (start, full0, full1, kdone):", b2,
-                h[b2 * 64] - t0, h[b2 * 64 + 1] - t0, h[b2 * 64 + 63] - t0);
-        for (int j = 0; j < 15; ++j)
-          if (h[b2 * 64 + 2 + 4 * j])
-            fprintf(stderr, " [%llu %llu %llu %llu]", h[b2 * 64 + 2 + 4 * j] - t0, h[b2 * 64 + 3 + 4 * j] - t0,
-                    h[b2 * 64 + 4 + 4 * j] - t0, h[b2 * 64 + 5 + 4 * j] - t0);
-        fprintf(stderr, "\n");
-      }
-    }
-  }
   return MLEGS_OK;
 }
 

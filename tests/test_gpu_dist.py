@@ -53,4 +53,8 @@ def test_distributed_parity(world, tmp_path, request):
     snaps = request.getfixturevalue("qvortex_snapshots")
     r = run_worker(world, snaps, tmp_path)
     print(r.stdout[-8000:])
+    logdir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(logdir):          # the full log travels back from the GPU box
+        with open(os.path.join(logdir, f"dist_worker_{world}gpu.log"), "w") as fh:
+            fh.write(r.stdout)
     assert r.returncode == 0 and "DIST WORKER OK" in r.stdout
