@@ -243,6 +243,13 @@ module mlegs_b200_c
       integer(c_int) :: rc
     end function
     !> MPI_Allreduce(sum) of n host doubles on the library's peer windows (check_stability, vortical_flow_3d.f90:404)
+    !> local azimuthal column j of s holds global m = loc_st(2) + stride*(j-1) (cyclic ownership on several ranks)
+    function mlegs_b200_dist_m_stride(s, stride) bind(C, name='mlegs_b200_dist_m_stride') result(rc)
+      import :: c_mlegs_field, c_int
+      type(c_mlegs_field), intent(in) :: s
+      integer(c_int), intent(out) :: stride
+      integer(c_int) :: rc
+    end function
     function mlegs_b200_dist_allreduce(buf, n) bind(C, name='mlegs_b200_dist_allreduce') result(rc)
       import :: c_double, c_int
       real(c_double), intent(inout) :: buf(*)

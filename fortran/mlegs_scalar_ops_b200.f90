@@ -108,13 +108,16 @@ contains
     complex(p8), dimension(:,:,:), allocatable, target :: loc
     complex(p8), dimension(:,:,:), allocatable :: part
     integer :: n
+    integer(c_int) :: ms
     allocate(array_glb(this%glb_sz(1), this%glb_sz(2), this%glb_sz(3)))
     allocate(part(this%glb_sz(1), this%glb_sz(2), this%glb_sz(3)))
     allocate(loc(this%loc_sz(1), this%loc_sz(2), this%loc_sz(3)))
     call to_c(this, c)
     call b200_check(mlegs_b200_field_download(c, c_loc(loc)))
+    call b200_check(mlegs_b200_dist_m_stride(c, ms))   ! azimuthal columns are owned cyclically on several ranks
     part = 0.D0
-    part(this%loc_st(1)+1:this%loc_st(1)+this%loc_sz(1), this%loc_st(2)+1:this%loc_st(2)+this%loc_sz(2), &
+    part(this%loc_st(1)+1:this%loc_st(1)+this%loc_sz(1), &
+         this%loc_st(2)+1:this%loc_st(2)+(this%loc_sz(2)-1)*ms+1:ms, &
          this%loc_st(3)+1:this%loc_st(3)+this%loc_sz(3)) = loc
     n = size(part)
     call MPI_reduce(part, array_glb, n, MPI_double_complex, MPI_sum, 0, comm_glb, MPI_err)
@@ -126,13 +129,16 @@ contains
     type(c_mlegs_field) :: c
     complex(p8), dimension(:,:,:), allocatable, target :: loc
     integer :: n
+    integer(c_int) :: ms
     if (.not. allocated(array_glb)) allocate(array_glb(this%glb_sz(1), this%glb_sz(2), this%glb_sz(3)))
     n = size(array_glb)
     call MPI_bcast(array_glb, n, MPI_double_complex, 0, comm_glb, MPI_err)
     allocate(loc(this%loc_sz(1), this%loc_sz(2), this%loc_sz(3)))
-    loc = array_glb(this%loc_st(1)+1:this%loc_st(1)+this%loc_sz(1), this%loc_st(2)+1:this%loc_st(2)+this%loc_sz(2), &
-                    this%loc_st(3)+1:this%loc_st(3)+this%loc_sz(3))
     call to_c(this, c)
+    call b200_check(mlegs_b200_dist_m_stride(c, ms))
+    loc = array_glb(this%loc_st(1)+1:this%loc_st(1)+this%loc_sz(1), &
+                    this%loc_st(2)+1:this%loc_st(2)+(this%loc_sz(2)-1)*ms+1:ms, &
+                    this%loc_st(3)+1:this%loc_st(3)+this%loc_sz(3))
     call b200_check(mlegs_b200_field_upload(c, c_loc(loc)))
     deallocate(loc)
   end procedure

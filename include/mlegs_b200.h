@@ -223,6 +223,14 @@ int mlegs_b200_msave_part(const mlegs_field *meta, const void *host_e, const cha
 int mlegs_b200_mload_part(const char *fn, mlegs_field *meta, void *host_e, int is_binary, int is_global, int rank);
 
 /* ---- multi-GPU (one process per GPU, slab over m) ------------------------------------ */
+/* Ownership of the azimuthal wavenumbers on several ranks.  The reference's decompose() (mlegs_envir_mpi.f90:6-31) hands
+ * out contiguous blocks; the work per column falls linearly with m (nn(m) = nrchop - m), so blocks leave rank 0 with
+ * 1.4x the mean radial-transform / axial-FFT / solve work at 8 ranks.  Here rank q owns m = q, q + P, q + 2P, ...:
+ * an m-distributed block has loc_st(2) = q (its first column) and its local column j holds global m = loc_st(2) +
+ * stride * j, stride = P.  Blocks that hold every column (PPP layout, one rank) have stride 1.  Everything inside the
+ * library (chop, transforms, operators, exchanges, msave/mload) follows this map; a host that indexes s%e by m itself
+ * must use it too. */
+int mlegs_b200_dist_m_stride(const mlegs_field *s, int *stride);
 /* CUDA-IPC plumbing for the fused FFT+transpose kernels: each rank exports the handle of its
  * exchange window, the host side all-gathers the 64-byte handles (torch.distributed / MPI)
  * and attaches them.  Replaces MPI_Alltoallw + derived datatypes (dist:468-504).            */
@@ -230,14 +238,16 @@ int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64
 int mlegs_b200_dist_attach(const unsigned char *handles64_all_ranks);
 int mlegs_b200_dist_detach(void);
 /* Host-only exchange plan (no CUDA needed): destination rank and linear index in that rank's new local block
- * for every element of rank `rank`'s local block in memory order; dir 0 = exchange(2,1), 1 = exchange(1,2).
- * The device put kernel runs the same addressing code (dist:395-504's subarray datatypes). */
+ * for every element of rank `rank`'s local block in memory order; dir 0 = exchange(2,1), 1 = exchange(1,2) (columns
+ * at their global positions: the user-visible s%exchange), 2 = exchange(1,2) into the transit layout of the exchanges
+ * fused into a transform (columns grouped by owning rank; the azimuthal FFT that follows reads them permuted).
+ * The device put kernels run the same addressing code (dist:395-504's subarray datatypes). */
 int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim, int nz, int *dst_rank,
                             long long *dst_index);
 /* Host-only plan of the STAGED exchange(1,2) (no CUDA needed): for every element of rank `rank`'s local
  * (nrdim, m_cnt, nz) block in memory order, its index inside the local staging buffer the Legendre synthesis writes
  * (stage_index), and -- for every staging index -- the rank and linear index the ship kernel moves it to
- * (ship_rank, ship_index; both of length nrdim*m_cnt*nz).  Composing the two must equal dist_put_map(dir = 1). */
+ * (ship_rank, ship_index; both of length nrdim*m_cnt*nz).  Composing the two must equal dist_put_map(dir = 2). */
 int mlegs_b200_dist_stage_map(int rank, int nranks, int nrdim, int npdim, int nz, long long *stage_index,
                               int *ship_rank, long long *ship_index);
 /* Sum n HOST doubles over all ranks on the library's own peer windows (the app-level MPI_Allreduce of

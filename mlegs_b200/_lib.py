@@ -112,6 +112,7 @@ _SIGS = {
     "mlegs_b200_dist_detach": (C.c_int, []),
     "mlegs_b200_dist_allreduce": (C.c_int, [C.c_void_p, C.c_int]),
     "mlegs_b200_dist_put_map": (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
+    "mlegs_b200_dist_m_stride": (C.c_int, [_P(Field), _P(C.c_int)]),
     "mlegs_b200_dist_stage_map": (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

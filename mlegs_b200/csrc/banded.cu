@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
   const size_t bsz = (size_t)KB * a.nrl;
   cplx *cur = bufs, *nxt = bufs + bsz, *s0 = bufs + 2 * bsz, *s2 = bufs + 3 * bsz;   // s0/s2 only with combine
   const int j = blockIdx.x, k0 = blockIdx.y * KB;
-  const int mglob = a.m0 + j;
+  const int mglob = a.m0 + j * a.ms;
   const int nn = nn_of(mglob, a.nrc, a.npc);
   constexpr int half = NB / 2;
   const double *tab = a.tab + (size_t)mglob * NB * a.ne;
@@ -264,7 +264,7 @@ int launch_band_op(const BandOpArgs &a, cudaStream_t st) {
   int threads = std::min(1024, (a.nrl + 31) / 32 * 32);
   // one pass over the retained lines (helmp's whole-array combination touches every line of the block)
   const double lines_b = a.combine ? (double)a.nrl * a.npl * a.nzl
-                                   : retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu);
+                                   : retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu, a.ms);
   prof_begin(a.combine ? "helmp_band" : (a.nb == 3 ? "xxdx_band" : "del2_band"), st, 32.0 * lines_b);
   if (a.nb == 3)
     band_op_kernel<3><<<grid, threads, smem, st>>>(a, KB);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
   for (int sys = blockIdx.x * SOLVE_WARPS + warp; sys < nsys; sys += gridDim.x * SOLVE_WARPS) {
     const int j = sys % a.npl;
     const int k = a.k0 + sys / a.npl;
-    const int mglob = a.m0 + j;
+    const int mglob = a.m0 + j * a.ms;
     const int nn = nn_of(mglob, a.nrc, a.npc);
     if (nn < 1) continue;
     double *ws = a.ws_global ? a.ws_global + (size_t)(blockIdx.x * SOLVE_WARPS + warp) * a.ws_doubles
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
     // consecutive systems of a block share the column j (same nn, neighbouring factor storage)
     const int j = sys / a.nk;
     const int kf = a.k0 + sys % a.nk;     // plane whose factors are used
-    const int mglob = a.m0 + j;
+    const int mglob = a.m0 + j * a.ms;
     const int nn = nn_of(mglob, a.nrc, a.npc);
     if (nn < 1) continue;
     const long long c0 = a.fac_off[j] + (long long)(kf - a.k0) * nn;
@@ -701,7 +701,7 @@ void band_solve_cache_enable(int on) {
 static SolveArgs key_of(const SolveArgs &a) {
   SolveArgs k;
   memset(&k, 0, sizeof(k));   // padding bytes too: keys are compared with memcmp
-  k.nrl = a.nrl; k.npl = a.npl; k.m0 = a.m0; k.k0 = a.k0; k.nk = a.nk; k.ne = a.ne;
+  k.nrl = a.nrl; k.npl = a.npl; k.m0 = a.m0; k.ms = a.ms; k.k0 = a.k0; k.nk = a.nk; k.ne = a.ne;
   k.nrc = a.nrc; k.npc = a.npc; k.nnmax = a.nnmax; k.kl = a.kl; k.ku = a.ku; k.power = a.power;
   k.add_alpha = a.add_alpha; k.alpha = a.alpha; k.beta = a.beta; k.special00 = a.special00;
   k.sp0 = a.sp0; k.sp1 = a.sp1; k.sp2 = a.sp2;   // preln_rhs only enters the right-hand side
@@ -736,7 +736,7 @@ int launch_band_solve_ranges(SolveArgs base, int n1, int kl_first, int lo, int n
   const bool have_a = n1 > 0, have_b = lo < nzl;
   size_t cols = 0;   // factor columns of the first range
   for (int j = 0; j < a.npl; ++j) {
-    const int m = a.m0 + j;
+    const int m = a.m0 + j * a.ms;
     cols += (size_t)((m < a.npc) ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0) * (size_t)std::max(n1, 0);
   }
   const size_t fbytes = cols * (size_t)(2 * a.kl + a.ku + 1) * sizeof(double);
@@ -796,7 +796,7 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
     // mirrored plane re-reads it from L2) + one read and one write of every right-hand side
     double syscols = 0.0;
     for (int j = 0; j < a.npl; ++j) {
-      const int m = a.m0 + j;
+      const int m = a.m0 + j * a.ms;
       syscols += (double)((m < a.npc) ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0) * a.nk;
     }
     const double rhs_cols = a.mirror_mode == 1 ? 2.0 * syscols : syscols;
@@ -815,7 +815,7 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
   if (g_fcache_on && a.kl <= 8) {
     std::vector<long long> off(a.npl + 1, 0);
     for (int j = 0; j < a.npl; ++j) {
-      int m = a.m0 + j;
+      int m = a.m0 + j * a.ms;
       int nn = (m < a.npc) ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
       off[j + 1] = off[j] + (long long)nn * a.nk;
     }

@@ -117,6 +117,10 @@ static int free_all() {
 }  // namespace mlegs
 
 namespace mlegs {
+int field_mstride(const mlegs_field *f) {
+  Context &c = ctx();
+  return (c.nranks > 1 && f->loc_sz[1] != c.npdim) ? c.nranks : 1;
+}
 void field_set_layout(mlegs_field *f, bool physical) {
   Context &c = ctx();
   f->glb_sz[0] = c.nrdim;
@@ -137,7 +141,7 @@ void field_set_layout(mlegs_field *f, bool physical) {
     f->loc_sz[1] = c.m_cnt[c.rank];
     f->loc_sz[2] = c.nzdim;
     f->loc_st[0] = 0;
-    f->loc_st[1] = c.m_off[c.rank];
+    f->loc_st[1] = c.nranks > 1 ? c.rank : 0;   // first column; the following ones are nranks apart
     f->loc_st[2] = 0;
     f->axis_comm[0] = 2;
     f->axis_comm[1] = 1;
@@ -244,7 +248,8 @@ int mlegs_b200_init(const mlegs_params *p, const double *x, const double *w, con
   c.m_off.resize(nranks);
   for (int q = 0; q < nranks; ++q) {
     decompose(c.nrdim, nranks, q, &c.r_cnt[q], &c.r_off[q]);
-    decompose(c.npdim, nranks, q, &c.m_cnt[q], &c.m_off[q]);
+    c.m_cnt[q] = q < c.npdim ? (c.npdim - q + nranks - 1) / nranks : 0;   // m = q, q + P, ...
+    c.m_off[q] = q == 0 ? 0 : c.m_off[q - 1] + c.m_cnt[q - 1];
   }
   // field-sized scratch: the larger of the two slab shapes
   size_t n_ppp = (size_t)c.r_cnt[0] * c.npdim * c.nzdim;

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) exchange_put_kernel(PeerTable t, const cp
     const int k = (int)(r / cols);
     int q;
     size_t dst;
-    slab_put_index(dir, me, t.nranks, t.r_cnt, t.r_off, t.m_cnt, t.m_off, nrdim, npdim, i, j, k, &q, &dst);
+    slab_put_index(dir, me, t.nranks, t.r_cnt, t.r_off, t.m_cnt, t.m_off, nrdim, npdim, i, j, k, &q, &dst, 1);
     cplx *w = reinterpret_cast<cplx *>(reinterpret_cast<char *>(t.base[q]) + t.data_off);
     w[dst] = src[idx];
   }
@@ -239,6 +239,13 @@ int mlegs_b200_exchange(mlegs_field *s, int axis_old, int axis_new) {
   return MLEGS_OK;
 }
 
+int mlegs_b200_dist_m_stride(const mlegs_field *s, int *stride) {
+  Context &c = ctx();
+  if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
+  *stride = field_mstride(s);
+  return MLEGS_OK;
+}
+
 int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64[64]) {
   Context &c = ctx();
   if (!c.ready) return fail(MLEGS_E_STATE, "mlegs_b200: transformation kit is not initialized");
@@ -301,12 +308,15 @@ int mlegs_b200_dist_detach(void) {
  * that rank's new local block.  Same code as the device put kernel. */
 int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim, int nz, int *dst_rank,
                             long long *dst_index) {
-  if (nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks || (dir != 0 && dir != 1))
+  if (nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks || dir < 0 || dir > 2)
     return fail(MLEGS_E_COMM, "mlegs_b200_dist_put_map: bad arguments");
+  const int natural = dir == 2 ? 0 : 1;   // dir 2: exchange(1,2) into the transit layout of the fused exchanges
+  if (dir == 2) dir = 1;
   int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
   for (int q = 0; q < nranks; ++q) {
     decompose(nrdim, nranks, q, &r_cnt[q], &r_off[q]);
-    decompose(npdim, nranks, q, &m_cnt[q], &m_off[q]);
+    m_cnt[q] = q < npdim ? (npdim - q + nranks - 1) / nranks : 0;   // cyclic: m = q, q + P, ...
+    m_off[q] = q == 0 ? 0 : m_off[q - 1] + m_cnt[q - 1];
   }
   const int rows = dir == 0 ? r_cnt[rank] : nrdim;
   const int cols = dir == 0 ? npdim : m_cnt[rank];
@@ -316,7 +326,7 @@ int mlegs_b200_dist_put_map(int dir, int rank, int nranks, int nrdim, int npdim,
       for (int i = 0; i < rows; ++i, ++idx) {
         int q;
         size_t dst;
-        slab_put_index(dir, rank, nranks, r_cnt, r_off, m_cnt, m_off, nrdim, npdim, i, j, k, &q, &dst);
+        slab_put_index(dir, rank, nranks, r_cnt, r_off, m_cnt, m_off, nrdim, npdim, i, j, k, &q, &dst, natural);
         dst_rank[idx] = q;
         dst_index[idx] = (long long)dst;
       }
@@ -332,7 +342,8 @@ int mlegs_b200_dist_stage_map(int rank, int nranks, int nrdim, int npdim, int nz
   int r_cnt[DIST_MAX_RANKS], r_off[DIST_MAX_RANKS], m_cnt[DIST_MAX_RANKS], m_off[DIST_MAX_RANKS];
   for (int q = 0; q < nranks; ++q) {
     decompose(nrdim, nranks, q, &r_cnt[q], &r_off[q]);
-    decompose(npdim, nranks, q, &m_cnt[q], &m_off[q]);
+    m_cnt[q] = q < npdim ? (npdim - q + nranks - 1) / nranks : 0;   // cyclic: m = q, q + P, ...
+    m_off[q] = q == 0 ? 0 : m_off[q - 1] + m_cnt[q - 1];
   }
   const int mc = m_cnt[rank];
   size_t idx = 0;

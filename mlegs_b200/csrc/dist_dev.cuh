@@ -44,20 +44,27 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // Destination of local element (i, j, k) of rank `me` in an exchange: owning rank q and linear index inside
-// q's new local block.  Shared by the put kernel and the host-side plan (mlegs_b200_dist_put_map), which the
-// CPU tests check against the reference's subarray semantics (dist:395-504).
-// dir 0: (2,1) exchange, src (r_loc, npdim, nz) -> (nrdim, m_cnt[q], nz);  dir 1: (1,2), src (nrdim, m_loc, nz)
-// -> (r_cnt[q], npdim, nz).
+// q's new local block.  Shared by the put kernels and the host-side plan (mlegs_b200_dist_put_map), which the
+// CPU tests check against the subarray semantics of dist:395-504.  The azimuthal columns are owned cyclically:
+// rank q holds m = q, q + P, ... as its local columns 0, 1, ...
+// dir 0: (2,1) exchange, src (r_loc, npdim, nz) -> (nrdim, m_cnt[q], nz): column m goes to rank m mod P, local
+//        column m / P.
+// dir 1: (1,2) exchange, src (nrdim, m_loc, nz) -> (r_cnt[q], npdim, nz).  natural != 0: local column j lands at its
+//        global position me + P j (the user-visible s%exchange).  natural == 0: the transit layout of the exchanges
+//        fused into a transform -- columns grouped by source rank, rank `me`'s at m_off[me] .. -- which keeps the
+//        columns a rank ships to a peer contiguous (long NVLink runs); the azimuthal FFT that follows reads its point
+//        m at window column m_off[m mod P] + m / P.
 __host__ __device__ inline void slab_put_index(int dir, int me, int nranks, const int *r_cnt, const int *r_off,
                                                const int *m_cnt, const int *m_off, int nrdim, int npdim, int i, int j,
-                                               int k, int *q_out, size_t *dst_out) {
+                                               int k, int *q_out, size_t *dst_out, int natural = 0) {
   int q = 0;
   if (dir == 0) {
-    while (q + 1 < nranks && j >= m_off[q + 1]) ++q;
-    *dst_out = ((size_t)k * m_cnt[q] + (j - m_off[q])) * nrdim + r_off[me] + i;
+    q = j % nranks;
+    *dst_out = ((size_t)k * m_cnt[q] + j / nranks) * nrdim + r_off[me] + i;
   } else {
     while (q + 1 < nranks && i >= r_off[q + 1]) ++q;
-    *dst_out = ((size_t)k * npdim + m_off[me] + j) * r_cnt[q] + (i - r_off[q]);
+    const int col = natural ? me + nranks * j : m_off[me] + j;
+    *dst_out = ((size_t)k * npdim + col) * r_cnt[q] + (i - r_off[q]);
   }
   *q_out = q;
 }

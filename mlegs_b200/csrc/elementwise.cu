@@ -29,7 +29,7 @@ __global__ void mask_kernel(MaskArgs a) {
     size_t t = idx / a.nrl;
     int j = (int)(t % a.npl);
     int k = (int)(t / a.npl);
-    int m = a.m0 + j;
+    int m = a.m0 + j * a.ms;
     bool z = false;
     if (a.row_mode) {
       int nn = 0;
@@ -54,7 +54,7 @@ int launch_mask(const MaskArgs &a, cudaStream_t st) {
     int kzm = 0;
     for (int k = 0; k < a.nzl; ++k) kzm += (k >= a.kz_lo && k < a.kz_hi) ? 1 : 0;
     for (int j = 0; j < a.npl; ++j) {
-      const int m = a.m0 + j;
+      const int m = a.m0 + j * a.ms;
       if (m >= a.col_cut) {
         zeroed += (double)a.nrl * a.nzl;
         continue;
@@ -80,7 +80,7 @@ int launch_mask(const MaskArgs &a, cudaStream_t st) {
 
 __device__ __forceinline__ double svv_q(const SvvArgs &a, int i, int j, int k) {
   double q_r = fmin(1.0, (double)max(a.r0 + i, 0) / a.qr_den);
-  double q_p = fmin(1.0, (double)abs(a.m0 + j) / a.qp_den);
+  double q_p = fmin(1.0, (double)abs(a.m0 + j * a.ms) / a.qp_den);
   double kv = (k < a.nak) ? fabs(a.ak[k]) : 0.0;
   double q_z = fmin(1.0, kv / a.kmax);
   return fmin(1.0, fmax(fmax(q_r, q_p), q_z));
@@ -227,13 +227,13 @@ int launch_calcat(cplx *e, int nrl, int npl, int nzl, int nrows, const double *a
 // ---------------------------------------------------------------------------------------------
 // delsqp / idelsqp, ops:327-416: e(n,m,:) *= -n'(n'+1)/ell^2 (or its inverse), n' = m + n
 // ---------------------------------------------------------------------------------------------
-__global__ void delsqp_kernel(cplx *e, int nrl, int npl, int nzl, int m0, int nrc, int npc, double ell2, int inverse) {
+__global__ void delsqp_kernel(cplx *e, int nrl, int npl, int nzl, int m0, int ms, int nrc, int npc, double ell2, int inverse) {
   const size_t n = (size_t)nrl * npl * nzl;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     int i = (int)(idx % nrl);
     size_t t = idx / nrl;
     int j = (int)(t % npl);
-    int m = m0 + j;
+    int m = m0 + j * ms;
     if (m >= npc) continue;
     int nn = min(nrc, nrc - m);
     if (i >= nn) continue;
@@ -255,11 +255,11 @@ __global__ void delsqp_kernel(cplx *e, int nrl, int npl, int nzl, int m0, int nr
   }
 }
 
-int launch_delsqp(cplx *e, int nrl, int npl, int nzl, int m0, int nrc, int npc, double ell2, int inverse,
+int launch_delsqp(cplx *e, int nrl, int npl, int nzl, int m0, int ms, int nrc, int npc, double ell2, int inverse,
                   cudaStream_t st) {
   size_t n = (size_t)nrl * npl * nzl;
-  prof_begin(inverse ? "idelsqp" : "delsqp", st, 32.0 * retained_elems(nrl, npl, nzl, 0, m0, nrc, npc, nzl, nzl));
-  delsqp_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(e, nrl, npl, nzl, m0, nrc, npc, ell2, inverse);
+  prof_begin(inverse ? "idelsqp" : "delsqp", st, 32.0 * retained_elems(nrl, npl, nzl, 0, m0, nrc, npc, nzl, nzl, ms));
+  delsqp_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(e, nrl, npl, nzl, m0, ms, nrc, npc, ell2, inverse);
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
@@ -458,7 +458,7 @@ __global__ void tp_combine_kernel(TpCombineArgs a) {
     size_t t = idx / a.nrl;
     int j = (int)(t % a.npl);
     int k = (int)(t / a.npl);
-    int m = a.m0 + j;
+    int m = a.m0 + j * a.ms;
     if (m >= a.npc) continue;
     int nn = min(a.nrc, a.nrc - m);
     if (i >= nn || !k_retained(k, a.nzc, a.nzcu)) continue;
@@ -489,7 +489,7 @@ __global__ void tp_combine_kernel(TpCombineArgs a) {
 int launch_tp_combine(const TpCombineArgs &a, cudaStream_t st) {
   size_t n = (size_t)a.nrl * a.npl * a.nzl;
   prof_begin("tp_combine", st, ((a.mode == 0 || a.mode == 2) ? 32.0 : 48.0) *
-                                   retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu));
+                                   retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu, a.ms));
   tp_combine_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(a);
   prof_end(st);
   KERNEL_CHECK();
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(128) fftreat_tail_kernel(FftreatArgs a) {
   __shared__ cplx buf[2][FFTREAT_MAXTAIL];
   const int line = blockIdx.x;
   const int j = line % a.npl, k = line / a.npl;
-  const int m = a.m0 + j;
+  const int m = a.m0 + j * a.ms;
   if (m >= a.npc) return;
   cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
   const bool kept = (k < a.nzc) || (k + 1 >= a.nzcu);
@@ -610,7 +610,7 @@ __global__ void tv_combine_kernel(TvCombineArgs a) {
     size_t t = idx / a.nrl;
     int j = (int)(t % a.npl);
     int k = (int)(t / a.npl);
-    int m = a.m0 + j;
+    int m = a.m0 + j * a.ms;
     if (m >= a.npc) continue;
     int nn = min(a.nrc, a.nrc - m);
     if (i >= nn || !k_retained(k, a.nzc, a.nzcu)) continue;
@@ -624,7 +624,7 @@ __global__ void tv_combine_kernel(TvCombineArgs a) {
 }
 int launch_tv_combine(const TvCombineArgs &a, cudaStream_t st) {
   size_t n = (size_t)a.nrl * a.npl * a.nzl;
-  prof_begin("tv_combine", st, 96.0 * retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu));
+  prof_begin("tv_combine", st, 96.0 * retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu, a.ms));
   tv_combine_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(a);
   prof_end(st);
   KERNEL_CHECK();

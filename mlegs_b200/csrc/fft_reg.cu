@@ -237,9 +237,14 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk)
   if (MODE == FFT_C2R_BWD) {
     // Hermitian half spectrum C_0..C_N -> shared, then the packed Z_m (conjugated for the conj-FFT-conj inverse).
     // Im(C_0), Im(C_N) are ignored like external/ffte-7.0/zdfft2d.f:119-128 does.
+    // column of point m inside the input block (transit layout of a fused exchange: grouped by owner of m)
+    auto colof = [&](int m) -> long long {
+      if (EXT && a.rs.perm_p > 1) return (long long)a.rs.perm_off[m % a.rs.perm_p] + m / a.rs.perm_p;
+      return m;
+    };
 #pragma unroll
-    for (int j = 0; j < E; ++j) v[j] = ok ? gin[(long long)(t + T * j) * a.stride_pt] : zero;
-    if (t == 0) nyq = ok ? gin[(long long)N * a.stride_pt] : zero;
+    for (int j = 0; j < E; ++j) v[j] = ok ? gin[colof(t + T * j) * a.stride_pt] : zero;
+    if (t == 0) nyq = ok ? gin[colof(N) * a.stride_pt] : zero;
 #pragma unroll
     for (int j = 0; j < E; ++j) sm[(t + T * j) * L + l] = v[j];
     if (t == 0) sm[N * L + l] = nyq;
@@ -413,7 +418,7 @@ template <int MODE, int N, int E, int THREADS>
 static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
   // the extended kernel only exists for the real modes (fused exchange: r2c; fused row scaling: r2c and c2r)
   if constexpr (MODE == FFT_R2C_FWD || MODE == FFT_C2R_BWD) {
-    if (a.use_peer || a.rs.mode != 0) return launch_one_ext<MODE, N, E, THREADS, true>(a, nfields, st);
+    if (a.use_peer || a.rs.mode != 0 || a.rs.perm_p > 1) return launch_one_ext<MODE, N, E, THREADS, true>(a, nfields, st);
   }
   return launch_one_ext<MODE, N, E, THREADS, false>(a, nfields, st);
 }

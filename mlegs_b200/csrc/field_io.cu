@@ -180,12 +180,14 @@ int msave_part(const mlegs_field *s, const cplx *host_e, const char *fn, int is_
     if (rc == MLEGS_OK) rc = pwrite_all(fd, head.data(), head.size(), 0, name.c_str());
     if (rc == MLEGS_OK) rc = pwrite_all(fd, tail.data(), tail.size(), head.size() + L.data, name.c_str());
   }
-  // position of the local block inside the array the file describes
+  // position of the local block inside the array the file describes; local column j is global column j0 + j ms
+  // (ms > 1: the cyclic azimuthal ownership of a multi-rank run, mlegs_internal.h)
   const int i0 = is_global ? s->loc_st[0] : 0, j0 = is_global ? s->loc_st[1] : 0, k0 = is_global ? s->loc_st[2] : 0;
+  const int ms = (is_global && ctx().ready) ? field_mstride(s) : 1;
   const int l1 = s->loc_sz[0], l2 = s->loc_sz[1], l3 = s->loc_sz[2];
   if (L.binary) {
     // runs of l1 contiguous elements; whole planes / the whole block when the leading extents are complete
-    const bool full1 = (l1 == L.n1), full2 = full1 && (l2 == L.n2);
+    const bool full1 = (l1 == L.n1) && ms == 1, full2 = full1 && (l2 == L.n2);
     for (int k = 0; k < l3 && rc == MLEGS_OK; ++k) {
       if (full2) {
         if (k > 0) break;
@@ -195,7 +197,7 @@ int msave_part(const mlegs_field *s, const cplx *host_e, const char *fn, int is_
       }
       for (int j = 0; j < l2 && rc == MLEGS_OK; ++j) {
         const size_t src = ((size_t)k * l2 + j) * l1;
-        const size_t dst = (((size_t)(k0 + k) * L.n2 + (j0 + j)) * L.n1 + i0) * sizeof(cplx);
+        const size_t dst = (((size_t)(k0 + k) * L.n2 + (j0 + j * ms)) * L.n1 + i0) * sizeof(cplx);
         if (full1) {   // columns j0..j0+l2-1 of plane k are one run
           rc = pwrite_all(fd, host_e + (size_t)k * l2 * l1, (size_t)l1 * l2 * sizeof(cplx), head.size() + dst,
                           name.c_str());
@@ -207,10 +209,26 @@ int msave_part(const mlegs_field *s, const cplx *host_e, const char *fn, int is_
   } else {
     // line (k, i): n2 pairs; this rank owns pairs j0 .. j0+l2-1 of lines i0 .. i0+l1-1 of planes k0 .. k0+l3-1
     std::vector<char> seg((size_t)l2 * 2 * NUMW + 2);
-    const bool ends_line = (j0 + l2 == L.n2);
+    const bool ends_line = l2 > 0 && (j0 + (l2 - 1) * ms + 1 == L.n2);
     for (int k = 0; k < l3 && rc == MLEGS_OK; ++k) {
       const size_t plane_off = head.size() + (size_t)(k0 + k) * ((size_t)L.n1 * L.line + L.blank);
-      for (int i = 0; i < l1 && rc == MLEGS_OK; ++i) {
+      for (int i = 0; i < l1 && rc == MLEGS_OK && ms > 1; ++i) {
+        // strided columns: one pair at a time; the owner of the last column also ends the line
+        for (int j = 0; j < l2 && rc == MLEGS_OK; ++j) {
+          const cplx v = host_e[((size_t)k * l2 + j) * l1 + i];
+          char *p = seg.data();
+          fmt_1pe(v.x, p);
+          fmt_1pe(v.y, p + NUMW);
+          size_t n = 2 * NUMW;
+          if (ends_line && j == l2 - 1) {
+            seg[n++] = ' ';
+            seg[n++] = '\n';
+          }
+          rc = pwrite_all(fd, seg.data(), n, plane_off + (size_t)(i0 + i) * L.line + (size_t)(j0 + j * ms) * 2 * NUMW,
+                          name.c_str());
+        }
+      }
+      for (int i = 0; i < l1 && rc == MLEGS_OK && ms == 1; ++i) {
         char *p = seg.data();
         for (int j = 0; j < l2; ++j) {
           const cplx v = host_e[((size_t)k * l2 + j) * l1 + i];
@@ -240,6 +258,7 @@ int mload_part(const char *fn, mlegs_field *s, cplx *host_e, int is_binary, int 
   const Layout L = make_layout(s, is_binary != 0, is_global != 0);
   const std::string name = is_global ? std::string(fn) : local_name(fn, rank);
   const int i0 = is_global ? s->loc_st[0] : 0, j0 = is_global ? s->loc_st[1] : 0, k0 = is_global ? s->loc_st[2] : 0;
+  const int ms = (is_global && ctx().ready) ? field_mstride(s) : 1;
   const int l1 = s->loc_sz[0], l2 = s->loc_sz[1], l3 = s->loc_sz[2];
   auto size_error = [&](const int *got) {
     char b[256];
@@ -260,7 +279,7 @@ int mload_part(const char *fn, mlegs_field *s, cplx *host_e, int is_binary, int 
     for (int k = 0; k < l3 && rc == MLEGS_OK; ++k)
       for (int j = 0; j < l2 && rc == MLEGS_OK; ++j)
         rc = pread_all(fd, host_e + ((size_t)k * l2 + j) * l1, (size_t)l1 * sizeof(cplx),
-                       L.header + (((size_t)(k0 + k) * L.n2 + (j0 + j)) * L.n1 + i0) * sizeof(cplx), name.c_str());
+                       L.header + (((size_t)(k0 + k) * L.n2 + (j0 + j * ms)) * L.n1 + i0) * sizeof(cplx), name.c_str());
     if (rc == MLEGS_OK) {
       char t[sizeof(double) + 3 * sizeof(int) + 3];
       rc = pread_all(fd, t, sizeof(t), L.header + L.data, name.c_str());
@@ -299,7 +318,8 @@ int mload_part(const char *fn, mlegs_field *s, cplx *host_e, int is_binary, int 
         if (rc == MLEGS_OK) re = strtod(tok, nullptr);
         if (rc == MLEGS_OK && fscanf(fp, "%127s", tok) != 1) rc = io_fail("mload_scalar: unexpected end of", name.c_str());
         if (rc == MLEGS_OK) im = strtod(tok, nullptr);
-        const int li = i - i0, lj = j - j0, lk = k - k0;
+        const int li = i - i0, lk = k - k0;
+        const int lj = (j >= j0 && (j - j0) % ms == 0) ? (j - j0) / ms : -1;
         if (rc == MLEGS_OK && li >= 0 && li < l1 && lj >= 0 && lj < l2 && lk >= 0 && lk < l3)
           host_e[((size_t)lk * l2 + lj) * l1 + li] = make_double2(re, im);
       }

@@ -27,6 +27,10 @@ struct RowScale {
   int mode = 0;
   unsigned mask = 0;     // bit i: scalar i of the batch is scaled
   int r0 = 0, nr = 0;
+  // c2r side only: the input is an exchange window in the transit layout of the fused exchange(1,2) -- columns grouped
+  // by source rank (dist_dev.cuh) -- so point m of a line is read at column perm_off[m mod perm_p] + m / perm_p
+  int perm_p = 0;
+  int perm_off[16];
 };
 
 // prof.cu: optional CUDA-event timing around each launch
@@ -37,10 +41,10 @@ void prof_end(cudaStream_t st);
 
 // elements (n, m, k) of a local (nrl, npl, nzl) spectral block that the truncation keeps: rows r0 + i < nn(m) of the
 // columns m0 + j < npc, planes k < nzc or k >= nzcu (host helper of the algorithmic-byte counts above)
-inline double retained_elems(int nrl, int npl, int nzl, int r0, int m0, int nrc, int npc, int nzc, int nzcu) {
+inline double retained_elems(int nrl, int npl, int nzl, int r0, int m0, int nrc, int npc, int nzc, int nzcu, int ms = 1) {
   double rows = 0.0;
   for (int j = 0; j < npl; ++j) {
-    const int m = m0 + j;
+    const int m = m0 + j * ms;
     int nn = m < npc ? (nrc < nrc - m ? nrc : nrc - m) : 0;
     nn -= r0;
     rows += nn < 0 ? 0 : (nn > nrl ? nrl : nn);
@@ -87,6 +91,7 @@ struct LegArgs {
   int nrl;               // leading dimension (rows) of in/out == nrdim
   int npl;               // local number of m columns
   int m0;                // global m of local column 0
+  int ms = 1;            // global m of local column j = m0 + j ms (ms = number of ranks when m is distributed: cyclic)
   int nzl;               // number of z planes (complex columns per m)
   int nrc, npc;          // chop limits incl. offsets: nn(m) = max(min(nrc, nrc-m),0) for m < npc
   int nrdim;
@@ -105,6 +110,7 @@ int launch_leg_backward(const LegArgs &a, cudaStream_t st);
 struct MaskArgs {
   cplx *e;
   int nrl, npl, nzl, r0, m0;
+  int ms = 1;            // column j holds m = m0 + j ms
   int row_mode;
   int nrc, npc_rows;
   int col_cut;
@@ -115,6 +121,7 @@ int launch_mask(const MaskArgs &a, cudaStream_t st);
 struct SvvArgs {
   cplx *e;
   int nrl, npl, nzl, r0, m0;
+  int ms = 1;
   const double *ak;
   int nak;
   double qr_den, qp_den, kmax, cutoff, strength;
@@ -124,7 +131,7 @@ int launch_svv_apply(const SvvArgs &a, cudaStream_t st);
 
 int launch_calcat(cplx *e, int nrl, int npl, int nzl, int nrows, const double *at, cplx *out, int subtract,
                   double at_first, cudaStream_t st);
-int launch_delsqp(cplx *e, int nrl, int npl, int nzl, int m0, int nrc, int npc, double ell2, int inverse,
+int launch_delsqp(cplx *e, int nrl, int npl, int nzl, int m0, int ms, int nrc, int npc, double ell2, int inverse,
                   cudaStream_t st);
 struct PokeArgs {
   int n;
@@ -152,6 +159,7 @@ int launch_col_update(cplx *col, int n, int mode, const double *v1, const double
 struct FftreatArgs {
   cplx *e;
   int nrl, npl, nzl, m0;
+  int ms = 1;
   int nr, ns, ns0;                       // 1-based ns = nr*3/4, ns0 = min(ns+4, nr) of ops:1015-1016
   int npc, nzc, nzcu;
   const double *x;                       // Gauss-Legendre nodes
@@ -164,6 +172,7 @@ struct TpCombineArgs {
   const cplx *t;                         // one of eomul(v,ur), oemul(d,up), oemul(d,ur), eomul(v,up), eomul(t,uz)
   int mode;                              // 0: dst=(-iu*mv)*t  1: dst-=t  2: dst=(iu*kv)*t  3: dst+=(mv*kv)*t  4: dst-=t
   int nrl, npl, nzl, m0;
+  int ms = 1;
   int nrc, npc, nzc, nzcu;
   const double *ak;
 };
@@ -172,6 +181,7 @@ struct TvCombineArgs {
   cplx *ur, *up;                         // in: xxdx(chi), xxdx(psi); out: combined
   const cplx *psi, *uz;                  // psi, chi
   int nrl, npl, nzl, m0;
+  int ms = 1;
   int nrc, npc, nzc, nzcu;
   const double *ak;
 };
@@ -181,6 +191,7 @@ int launch_tv_combine(const TvCombineArgs &a, cudaStream_t st);
 struct BandOpArgs {
   cplx *e;
   int nrl, npl, nzl, m0;
+  int ms = 1;            // column j holds m = m0 + j ms
   const double *tab;     // (ne, nb, npchop) band coefficients
   int nb, ne;
   const double *ak;      // nullptr: no -ak^2 on the diagonal (xxdx, del2h)
@@ -196,6 +207,7 @@ int launch_band_op(const BandOpArgs &a, cudaStream_t st);
 struct SolveArgs {
   cplx *e;
   int nrl, npl, m0;
+  int ms;                // column j holds m = m0 + j ms
   int k0, nk;            // axial planes k0 .. k0+nk-1
   const double *tab;     // del2h table
   int ne;

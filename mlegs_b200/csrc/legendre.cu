@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_forward_kernel(LegArgs a) 
   const int par = warp >> 2, wr = (warp >> 1) & 1, wc = warp & 1;
   // scalars of one launch are neighbours in the grid so that they share the table slice of their m in L2
   const int fld = blockIdx.z % a.fb.n, ml = blockIdx.z / a.fb.n;
-  const int mglob = a.m0 + ml;
+  const int mglob = a.m0 + ml * a.ms;
   const int nn = (a.skip_m0 && mglob == 0) ? 0 : nn_of_m(mglob, a.nrc, a.npc);
   const int n0 = blockIdx.y * LEG_MT_F;
   const int kz0 = blockIdx.x * LEG_NTC;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(LEG_THREADS, 2) leg_backward_kernel(LegArgs a,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int par = warp >> 2, wr = (warp >> 1) & 1, wc = warp & 1;
   const int fld = blockIdx.z % a.fb.n, ml = blockIdx.z / a.fb.n;
-  const int mglob = a.m0 + ml;
+  const int mglob = a.m0 + ml * a.ms;
   const int nn = nn_of_m(mglob, a.nrc, a.npc);
   const int i0 = blockIdx.y * LEG_MT_B;
   const int kz0 = blockIdx.x * LEG_NTC;

@@ -155,7 +155,7 @@ __device__ __forceinline__ void bwd_fetch(const LegArgs &a, const LegItemsB &L, 
   const int itile = rest % L.nit;
   rest /= L.nit;
   const int fld = rest % L.nfld, ml = rest / L.nfld;
-  const int mglob = a.m0 + ml;
+  const int mglob = a.m0 + ml * a.ms;
   cx->i0 = itile * WSB_MT;
   cx->kz0 = kzt * NTC;
   cx->pf = a.pf + (size_t)mglob * a.nrh * a.ne + cx->i0;
@@ -428,7 +428,7 @@ __device__ __forceinline__ void fwd_fetch(const LegArgs &a, const LegItemsF &L, 
     const int kzt = rest % L.nkz;
     rest /= L.nkz;
     const int fld = rest % L.nfld, ml = L.mlo + rest / L.nfld;
-    const int mglob = a.m0 + ml;
+    const int mglob = a.m0 + ml * a.ms;
     const int nn = ws_nn_of_m(mglob, a.nrc, a.npc);
     if (r * WSF_MT >= nn) continue;      // nothing retained in this row tile: the last row tile with work zero-fills it
     cx->kz0 = kzt * NTC;
@@ -769,7 +769,7 @@ int launch_slab_ship(const PeerTable &t, const FieldBatch &fb, cudaStream_t st);
 void leg_alg_work(const LegArgs &a, double *bytes, double *flops) {
   double S = 0.0, cols = 0.0;
   for (int ml = 0; ml < a.npl; ++ml) {
-    const int m = a.m0 + ml;
+    const int m = a.m0 + ml * a.ms;
     const int nn = m < a.npc ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
     if (nn > 0 && !(a.skip_m0 && m == 0)) {
       S += nn;
@@ -804,7 +804,7 @@ int launch_leg_backward_ws(const LegArgs &a, cudaStream_t st) {
   L.nfld = a.fb.n;
   L.mcount = 0;
   for (int ml = 0; ml < a.npl; ++ml) {   // nn(m) is non-increasing in m: the columns with work form a prefix
-    const int m = a.m0 + ml;
+    const int m = a.m0 + ml * a.ms;
     const int nn = m < a.npc ? std::max(std::min(a.nrc, a.nrc - m), 0) : 0;
     if (nn <= 0) break;
     ++L.mcount;
@@ -859,7 +859,7 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   L.nfld = a.fb.n;
   L.mlo = (a.skip_m0 && a.m0 == 0) ? 1 : 0;
   auto nn_host = [&](int ml) {
-    const int m = a.m0 + ml;
+    const int m = a.m0 + ml * a.ms;
     return m < a.npc ? std::min(std::max(std::min(a.nrc, a.nrc - m), 0), a.nrdim) : 0;
   };
   int mcount = 0;

@@ -104,7 +104,11 @@ struct Context {
   std::vector<void *> peer_flags;
   void *d_flags = nullptr;
   unsigned long long epoch = 0;
-  std::vector<int> r_cnt, r_off, m_cnt, m_off;   // decompose() shares of nrdim / npdim
+  // r: decompose() shares of nrdim (mlegs_envir_mpi.f90:6-31).  m: CYCLIC ownership -- rank q holds the columns
+  // m = q, q + P, ... (m_cnt[q] of them) -- because the work per column falls linearly with m (nn(m) = nrchop - m):
+  // contiguous blocks give rank 0 1.4x the mean radial-transform / axial-FFT / solve work at 8 ranks.  m_off = prefix
+  // sums of m_cnt: where rank q's columns sit in an exchange window that groups columns by source rank.
+  std::vector<int> r_cnt, r_off, m_cnt, m_off;
 };
 
 Context &ctx();
@@ -127,6 +131,9 @@ struct ChopIdx {
 };
 int chop_index(const mlegs_field *s, ChopIdx *ci);
 void field_set_layout(mlegs_field *f, bool physical);
+// global m of local column j of a block = loc_st[1] + j * field_mstride: 1 when the block holds every azimuthal column,
+// the number of ranks when m is distributed (cyclic ownership: rank q holds m = q, q + P, q + 2P, ...)
+int field_mstride(const mlegs_field *f);
 int validate_params(const mlegs_params *p);
 
 }  // namespace mlegs

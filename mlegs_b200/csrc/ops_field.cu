@@ -90,6 +90,7 @@ int chop_impl(mlegs_field *s) {
   a.nzl = s->loc_sz[2];
   a.r0 = s->loc_st[0];
   a.m0 = s->loc_st[1];
+  a.ms = field_mstride(s);
   a.row_mode = s->space[0] == 'F';
   a.nrc = ci.nrc;
   a.npc_rows = ci.npc;
@@ -112,6 +113,7 @@ int dealias_impl(mlegs_field *s) {
   a.nzl = s->loc_sz[2];
   a.r0 = s->loc_st[0];
   a.m0 = s->loc_st[1];
+  a.ms = field_mstride(s);
   a.row_mode = 0;
   a.nrc = a.npc_rows = 0;
   a.col_cut = INT_MAX;
@@ -144,6 +146,7 @@ int svv_impl(mlegs_field *s, double *gain) {
   a.nzl = s->loc_sz[2];
   a.r0 = s->loc_st[0];
   a.m0 = s->loc_st[1];
+  a.ms = field_mstride(s);
   a.ak = c.d_ak;
   a.nak = c.p.nz;
   a.qr_den = std::max((double)(c.p.nrchop - 1), 1.0);
@@ -235,6 +238,7 @@ int fftreat_impl(mlegs_field *s) {
   a.npl = s->loc_sz[1];
   a.nzl = s->loc_sz[2];
   a.m0 = s->loc_st[1];
+  a.ms = field_mstride(s);
   a.nr = c.p.nr;
   a.ns = c.p.nr * 3 / 4;
   a.ns0 = std::min(a.ns + 4, c.p.nr);
@@ -264,7 +268,7 @@ int delsqp_impl(mlegs_field *s, bool inverse) {
     ln_new = v.x * ell2 * std::exp(c.h_lognorm[0]);   // ops:392
   }
   if (inverse) MLEGS_TRY(allreduce_host(&ln_new, 1));   // ops:394
-  MLEGS_TRY(launch_delsqp((cplx *)s->e, s->loc_sz[0], s->loc_sz[1], s->loc_sz[2], s->loc_st[1], ci.nrc, ci.npc,
+  MLEGS_TRY(launch_delsqp((cplx *)s->e, s->loc_sz[0], s->loc_sz[1], s->loc_sz[2], s->loc_st[1], field_mstride(s), ci.nrc, ci.npc,
                           ell2, inverse ? 1 : 0, strm()));
   if (own) {
     if (!inverse) {
@@ -295,6 +299,7 @@ static int band_args(const mlegs_field *s, BandOpArgs *a) {
   a->npl = s->loc_sz[1];
   a->nzl = s->loc_sz[2];
   a->m0 = s->loc_st[1];
+  a->ms = field_mstride(s);
   a->ne = c.ne;
   a->nrc = ci.nrc;
   a->npc = ci.npc;
@@ -386,6 +391,7 @@ static int solve_args(const mlegs_field *s, const ChopIdx &ci, SolveArgs *a) {
   a->nrl = s->loc_sz[0];
   a->npl = s->loc_sz[1];
   a->m0 = s->loc_st[1];
+  a->ms = field_mstride(s);
   a->tab = c.d_del2h;
   a->ne = c.ne;
   a->ak = c.d_ak;
@@ -743,6 +749,7 @@ int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr,
   t.npl = ur->loc_sz[1];
   t.nzl = ur->loc_sz[2];
   t.m0 = ur->loc_st[1];
+  t.ms = field_mstride(ur);
   t.nrc = ci.nrc;
   t.npc = ci.npc;
   t.nzc = ci.nzc;
@@ -842,6 +849,7 @@ int vec2tp_impl(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field 
   g.nrl = ur.loc_sz[0];
   g.npl = ur.loc_sz[1];
   g.m0 = ur.loc_st[1];
+  g.ms = field_mstride(&ur);
   g.nzl = ur.loc_sz[2];
   g.nrc = ci.nrc;
   g.npc = ci.npc;
@@ -857,6 +865,7 @@ int vec2tp_impl(const mlegs_field *vr, const mlegs_field *vp, const mlegs_field 
   t.npl = g.npl;
   t.nzl = g.nzl;
   t.m0 = g.m0;
+  t.ms = g.ms;
   t.nrc = ci.nrc;
   t.npc = ci.npc;
   t.nzc = ci.nzc;

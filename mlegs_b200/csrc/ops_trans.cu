@@ -32,6 +32,14 @@ static void set_space(mlegs_field *s, int id) {
   for (int a = 0; a < 3; ++a) s->axis_comm[a] = labels[id][a];
 }
 
+// the azimuthal c2r FFT that follows a fused exchange(1,2) reads the window's transit layout (columns grouped by the
+// rank that owns them, dist_dev.cuh)
+static void set_transit_perm(RowScale *rs) {
+  Context &c = ctx();
+  rs->perm_p = c.nranks;
+  for (int q = 0; q < c.nranks && q < 16; ++q) rs->perm_off[q] = c.m_off[q];
+}
+
 static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
   Context &c = ctx();
   int nrc = c.p.nrchop + s->nrchop_offset;
@@ -47,6 +55,7 @@ static int rtrans_args(const mlegs_field *s, const char *who, LegArgs *a) {
   a->nrl = s->loc_sz[0];
   a->npl = s->loc_sz[1];
   a->m0 = s->loc_st[1];
+  a->ms = field_mstride(s);
   a->nzl = s->loc_sz[2];
   a->nrc = nrc;
   a->npc = npc;
@@ -88,11 +97,11 @@ static int stage_z_compact(const mlegs_field *s, bool forward, const cplx *src, 
   Context &c = ctx();
   cudaStream_t st = (cudaStream_t)c.stream;
   const int nrc = c.p.nrchop + s->nrchop_offset, npc = c.p.npchop + s->npchop_offset;
-  const int npl = s->loc_sz[1], m0 = s->loc_st[1];
+  const int npl = s->loc_sz[1], m0 = s->loc_st[1], ms = field_mstride(s);
   if (c.cs_nrc != nrc || c.cs_npc != npc || c.cs_ncols != npl || !c.d_colstart) {
     std::vector<int> h(npl + 1, 0);
     for (int j = 0; j < npl; ++j) {
-      int m = m0 + j;
+      int m = m0 + j * ms;
       int nn = (m < npc) ? std::max(std::min(nrc, nrc - m), 0) : 0;
       nn = std::min(nn, s->loc_sz[0]);
       h[j + 1] = h[j] + nn;
@@ -204,7 +213,7 @@ int trans_impl(mlegs_field *s, const char *to) {
           at = o;
         }
       } else if (cur == 2) {
-        if (multi && dst == 0) {
+        if (multi && dst == 0 && fft_reg_supported(c.plan_p.n)) {
           // the epilogue's stores ARE the (1,2) exchange (rows go to the ranks that own them in physical space)
           PeerTable pt;
           void *landed = nullptr;
@@ -226,7 +235,9 @@ int trans_impl(mlegs_field *s, const char *to) {
               at = (cplx *)landed;
             }
             cplx *o = home;
-            MLEGS_TRY(stage_phi(s, false, at, o));
+            RowScale rs;
+            if (exchanged) set_transit_perm(&rs);   // the window holds the transit layout of the fused exchange
+            MLEGS_TRY(stage_phi(s, false, at, o, nullptr, exchanged ? &rs : nullptr));
             at = o;
           } else {
             cplx *o = home;
@@ -296,7 +307,7 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst, const Tra
     rs.mask = (opt->rs_mask >> i0) & ((1u << n) - 1u);
     rs.nr = c.p.nr;
   }
-  bool rows_zero = false;
+  bool rows_zero = false, in_transit = false;
   const mlegs_field *s0 = s[0];
   auto other = [&](int i) { return at[i] == home[i] ? tmp[i] : home[i]; };
   // batch reading from where the data is and writing in place, or to the buffer the data is not in
@@ -377,6 +388,7 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst, const Tra
           make(false, &fb);   // the other buffer of every scalar stages its rows in destination order
           MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, &pt, &fb));
           landed_in_window(landed, true);
+          in_transit = true;                // columns grouped by owner: the azimuthal FFT below reads them permuted
         } else {
           make(false, &fb);
           MLEGS_TRY(stage_r(s0, false, nullptr, nullptr, nullptr, &fb));
@@ -389,6 +401,7 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst, const Tra
           for (int i = 0; i < n; ++i) fb.out[i] = home[i];
         rs.mode = rs.mask ? 2 : 0;
         rs.r0 = s[0]->loc_st[0];
+        if (in_transit) set_transit_perm(&rs);
         MLEGS_TRY(stage_phi(s[0], false, nullptr, nullptr, &fb, &rs));
         moved(fb);
       }

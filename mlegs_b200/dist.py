@@ -21,6 +21,12 @@ def decompose(nsize: int, nprocs: int, proc: int):
     return (q + 1, (q + 1) * proc) if r > proc else (q, q * proc + r)
 
 
+def m_owned(npdim: int, nprocs: int, proc: int) -> range:
+    """Azimuthal columns of rank `proc` when m is distributed: cyclic, m = proc, proc + nprocs, ... (the work per
+    column falls linearly with m, so contiguous blocks would be unbalanced; include/mlegs_b200.h)."""
+    return range(proc, npdim, nprocs)
+
+
 def attach(group=None):
     """Export this rank's window, all-gather the IPC handles over `group`, map the peers' windows."""
     import torch.distributed as dist
@@ -49,11 +55,12 @@ def allreduce(values) -> np.ndarray:
 
 
 def put_map(direction: int, rank: int, nranks: int, nrdim: int, npdim: int, nz: int):
-    """Host-only exchange plan of one rank (no CUDA): (dst_rank, dst_index) per local element."""
+    """Host-only exchange plan of one rank (no CUDA): (dst_rank, dst_index) per local element.  direction 0:
+    exchange(2,1); 1: exchange(1,2); 2: exchange(1,2) into the transit layout of the fused exchanges."""
     if direction == 0:
         n = decompose(nrdim, nranks, rank)[0] * npdim * nz
     else:
-        n = nrdim * decompose(npdim, nranks, rank)[0] * nz
+        n = nrdim * len(m_owned(npdim, nranks, rank)) * nz
     dst_rank = np.zeros(n, dtype=np.int32)
     dst_index = np.zeros(n, dtype=np.int64)
     check(_lib.lib().mlegs_b200_dist_put_map(direction, rank, nranks, nrdim, npdim, nz,
@@ -65,7 +72,7 @@ def put_map(direction: int, rank: int, nranks: int, nrdim: int, npdim: int, nz: 
 def stage_map(rank: int, nranks: int, nrdim: int, npdim: int, nz: int):
     """Host-only plan of the staged exchange(1,2) of one rank (no CUDA): stage_index per local element, and
     (ship_rank, ship_index) per staging index."""
-    n = nrdim * decompose(npdim, nranks, rank)[0] * nz
+    n = nrdim * len(m_owned(npdim, nranks, rank)) * nz
     stage_index = np.zeros(n, dtype=np.int64)
     ship_rank = np.full(n, -1, dtype=np.int32)
     ship_index = np.full(n, -1, dtype=np.int64)

@@ -66,8 +66,7 @@ def msave_global(meta: Field, block: np.ndarray, fn: str, is_binary=False, group
 def assemble(s, group=None) -> np.ndarray:
     """scalar_assemble (dist:70-203): the global array, on every rank (slabs summed into zeros over `group`)."""
     glb = np.zeros(s.glb_sz, dtype=np.complex128, order="F")
-    st, sz = s.loc_st, s.loc_sz
-    glb[st[0]:st[0] + sz[0], st[1]:st[1] + sz[1], st[2]:st[2] + sz[2]] = s.download()
+    glb[s.global_slices()] = s.download()
     try:
         import torch
         import torch.distributed as dist

@@ -61,10 +61,22 @@ class Scalar:
         check(_lib.lib().mlegs_b200_field_upload(C.byref(self.f), a.ctypes.data_as(C.c_void_p)))
         return self
 
+    @property
+    def m_stride(self) -> int:
+        """Local azimuthal column j holds global m = loc_st[1] + m_stride * j (the number of ranks when m is distributed:
+        cyclic ownership, include/mlegs_b200.h; 1 otherwise)."""
+        v = C.c_int(1)
+        check(_lib.lib().mlegs_b200_dist_m_stride(C.byref(self.f), C.byref(v)))
+        return v.value
+
+    def global_slices(self):
+        """Index of this rank's block inside the global array."""
+        st, sz, ms = self.loc_st, self.loc_sz, self.m_stride
+        return (slice(st[0], st[0] + sz[0]), slice(st[1], st[1] + sz[1] * ms, ms), slice(st[2], st[2] + sz[2]))
+
     def upload_global(self, glb: np.ndarray) -> "Scalar":
         """disassemble (dist:205-368) without the gather: every rank holds the global array and keeps its slab."""
-        st, sz = self.loc_st, self.loc_sz
-        return self.upload(glb[st[0]:st[0] + sz[0], st[1]:st[1] + sz[1], st[2]:st[2] + sz[2]])
+        return self.upload(glb[self.global_slices()])
 
     def download(self) -> np.ndarray:
         out = np.empty(self.loc_sz, dtype=np.complex128, order="F")

@@ -25,8 +25,7 @@ TOL = 1.0e-12
 
 
 def slab(s: mb.Scalar, glb: np.ndarray) -> np.ndarray:
-    st, sz = s.loc_st, s.loc_sz
-    return glb[st[0]:st[0] + sz[0], st[1]:st[1] + sz[1], st[2]:st[2] + sz[2]]
+    return glb[s.global_slices()]
 
 
 def check(name, s: mb.Scalar, glb: np.ndarray, tol=TOL, exact=False):

@@ -30,37 +30,42 @@ def _worker(rank, world, port, glb_sz, q):
         i, j, k = np.meshgrid(np.arange(nrdim), np.arange(npdim), np.arange(nz), indexing="ij")
         full = np.asfortranarray((i * 1e4 + j * 1e2 + k) + 1j * (k * 1e4 + i * 1e2 + j))
         errs = []
-        for direction, (axis_old, axis_new) in enumerate([(2, 1), (1, 2)]):
-            # before: all of axis_old local, axis_new distributed
-            cnt, off = mdist.decompose(glb_sz[axis_new - 1], world, rank)
-            assert (cnt, off) == mo.decompose(glb_sz[axis_new - 1], world, rank)
+        # r is distributed with the reference's decompose (mlegs_envir_mpi.f90:6-31); m cyclically (rank q owns
+        # m = q, q + P, ...: include/mlegs_b200.h), so "the block of rank p" along m is full[:, p::P, :]
+        def block(axis, p):
             sl = [slice(None)] * 3
-            sl[axis_new - 1] = slice(off, off + cnt)
-            mine = np.asfortranarray(full[tuple(sl)])
+            if axis == 1:
+                c, o = mdist.decompose(nrdim, world, p)
+                assert (c, o) == mo.decompose(nrdim, world, p)
+                sl[0] = slice(o, o + c)
+            else:
+                own = mdist.m_owned(npdim, world, p)
+                sl[1] = slice(own.start, own.stop, own.step)
+            return np.asfortranarray(full[tuple(sl)])
+
+        for direction, (axis_old, axis_new) in enumerate([(2, 1), (1, 2), (1, 2)]):
+            # before: all of axis_old local, axis_new distributed; direction 2 = (1,2) into the transit layout
+            mine = block(axis_new, rank)
             dst_rank, dst_index = mdist.put_map(direction, rank, world, nrdim, npdim, nz)
             flat = mine.ravel(order="F")
             msgs = [(dst_index[dst_rank == p], flat[dst_rank == p]) for p in range(world)]
             # the all-to-all: every rank receives the messages addressed to it
             gathered = [None] * world
             dist.all_gather_object(gathered, msgs)
-            cnt_new, off_new = mdist.decompose(glb_sz[axis_old - 1], world, rank)
-            shp = list(glb_sz)
-            shp[axis_old - 1] = cnt_new
-            got = np.full(int(np.prod(shp)), np.nan + 0j)
+            want = block(axis_old, rank)       # reference meaning: all of axis_new, this rank's share of axis_old
+            if direction == 2:                 # columns grouped by the rank that owns them
+                order = np.concatenate([np.arange(npdim)[p::world] for p in range(world)])
+                want = np.asfortranarray(want[:, order, :])
+            got = np.full(want.size, np.nan + 0j)
             for src in range(world):
                 idx, val = gathered[src][rank]
                 assert not np.isfinite(got[idx]).any(), "two sources wrote the same element"
                 got[idx] = val
-            got = got.reshape(shp, order="F")
-            # reference meaning
-            blocks_old = []
-            for p in range(world):
-                c, o = mo.decompose(glb_sz[axis_new - 1], world, p)
-                s2 = [slice(None)] * 3
-                s2[axis_new - 1] = slice(o, o + c)
-                blocks_old.append(np.asfortranarray(full[tuple(s2)]))
-            want = mo.exchange_global(blocks_old, glb_sz, axis_old, axis_new)[rank]
-            errs.append(float(np.abs(got - want).max()) if got.shape == want.shape else 1e300)
+            got = got.reshape(want.shape, order="F")
+            errs.append(float(np.abs(got - want).max()))
+        # with contiguous ownership the same plan is the reference's scalar_exchange (dist:6-67): on ONE rank
+        blocks = [np.asfortranarray(full)]
+        assert np.array_equal(mo.exchange_global(blocks, glb_sz, 2, 1)[0], full)
         q.put((rank, errs))
     finally:
         dist.destroy_process_group()
@@ -81,7 +86,7 @@ def test_exchange_plan_matches_reference_semantics(glb_sz, world):
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, errs in results:
-        assert errs == [0.0, 0.0], (rank, errs)   # bit-exact data movement
+        assert errs == [0.0, 0.0, 0.0], (rank, errs)   # bit-exact data movement
 
 
 def test_decompose_covers_the_axis():
@@ -97,12 +102,12 @@ def test_decompose_covers_the_axis():
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_staged_exchange_equals_direct_put(world):
     """The staged exchange(1,2) (Legendre epilogue -> local staging buffer in destination order -> ship kernel's
-    contiguous runs) must deliver every element exactly where the direct put does; the staging map is a
+    contiguous runs) must deliver every element exactly where the direct put into the transit layout does; the staging map is a
     permutation of the local block and every ship run is contiguous on both sides."""
     from mlegs_b200 import dist as mdist
     nrdim, npdim, nz = 35, 9, 4
     for rank in range(world):
-        dst_rank, dst_index = mdist.put_map(1, rank, world, nrdim, npdim, nz)
+        dst_rank, dst_index = mdist.put_map(2, rank, world, nrdim, npdim, nz)
         stage, ship_rank, ship_index = mdist.stage_map(rank, world, nrdim, npdim, nz)
         n = stage.size
         assert n == dst_rank.size
