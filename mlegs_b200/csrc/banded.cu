@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
   for (int kk = 0; kk < KB; ++kk) {
     const int k = k0 + kk;
     if (k >= a.nzl) break;
-    const cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
+    const cplx *col = ((a.combine && a.src) ? a.src : a.e) + ((size_t)k * a.npl + j) * a.nrl;
     for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
       cplx v = col[i];
       cur[kk * a.nrl + i] = v;

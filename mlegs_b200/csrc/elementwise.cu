@@ -341,6 +341,8 @@ int launch_vecprod(cplx *vr, cplx *vp, cplx *vz, const cplx *ur, const cplx *up,
 //   mode 6: out = sp + beta*s2 + alpha*s     (helmp, ops:893)
 //   mode 7: y = y + dt*(x1 + c*x2)           (fefe: s + dt*(nl + hv*svis), ops:1086-1089)
 //   mode 8: y = y + a*(1.5*(x1 + c*x2) - 0.5*(x3 + d*x4))   (abab, ops:1147)
+//   mode 9: y = a*((y + d*(1.5*x1 - 0.5*x2)) + b*(c*x3))   (abcn: modes 3 and 5 in one pass, ops:1214 + 1229/1251;
+//           the inner sum is rounded to double exactly where the reference stores it in sh%e)
 // ---------------------------------------------------------------------------------------------
 
 __global__ void lincomb_kernel(LinArgs p) {
@@ -381,6 +383,12 @@ __global__ void lincomb_kernel(LinArgs p) {
         o = make_double2((sp.x + p.b * s2.x) + p.a * s.x, (sp.y + p.b * s2.y) + p.a * s.y);
         break;
       }
+      case 9: {
+        cplx nl = p.x1[idx], nlp = p.x2[idx], sv = p.x3[idx];
+        const double tr = y.x + p.d * (1.5 * nl.x - 0.5 * nlp.x), ti = y.y + p.d * (1.5 * nl.y - 0.5 * nlp.y);
+        o = make_double2(p.a * (tr + p.b * (p.c * sv.x)), p.a * (ti + p.b * (p.c * sv.y)));
+        break;
+      }
       case 8: {
         cplx x1 = p.x1[idx], x2 = p.x2[idx], x3 = p.x3[idx], x4 = p.x4[idx];
         o = make_double2(y.x + p.a * (1.5 * (x1.x + p.c * x2.x) - 0.5 * (x3.x + p.d * x4.x)),
@@ -400,8 +408,8 @@ __global__ void lincomb_kernel(LinArgs p) {
 int launch_lincomb(const LinArgs &p, cudaStream_t st) {
   if (!p.n) return MLEGS_OK;
   // fields read (incl. y where the mode needs it) + one written
-  static const int reads[9] = {2, 2, 2, 3, 1, 2, 3, 3, 5};
-  prof_begin("lincomb", st, 16.0 * (double)p.n * (reads[p.mode < 0 || p.mode > 8 ? 7 : p.mode] + 1));
+  static const int reads[10] = {2, 2, 2, 3, 1, 2, 3, 3, 5, 4};
+  prof_begin("lincomb", st, 16.0 * (double)p.n * (reads[p.mode < 0 || p.mode > 9 ? 7 : p.mode] + 1));
   lincomb_kernel<<<ew_grid(p.n), EW_THREADS, 0, st>>>(p);
   prof_end(st);
   KERNEL_CHECK();

@@ -190,6 +190,7 @@ int launch_tv_combine(const TvCombineArgs &a, cudaStream_t st);
 // ---- banded.cu --------------------------------------------------------------------------
 struct BandOpArgs {
   cplx *e;
+  const cplx *src = nullptr;   // helmp only (combine != 0): planes are read from here instead of e (replaces a field copy)
   int nrl, npl, nzl, m0;
   int ms = 1;            // column j holds m = m0 + j ms
   const double *tab;     // (ne, nb, npchop) band coefficients

@@ -356,7 +356,9 @@ int del2_impl(mlegs_field *s, bool horizontal) {
   return launch_band_op(a, strm());
 }
 
-int helmp_impl(mlegs_field *s, int power, double alpha, double beta) {
+int helmp_impl(mlegs_field *s, int power, double alpha, double beta, const void *src = nullptr);
+// src != nullptr: the operand is read from there (same layout as s) and the result written to s%e
+int helmp_impl(mlegs_field *s, int power, double alpha, double beta, const void *src) {
   MLEGS_TRY(ready());
   Context &c = ctx();
   if (!((power % 2 == 0) && power >= 4)) return fail(MLEGS_E_ARG, "helmp: even power greater than or equal to 4");
@@ -370,6 +372,7 @@ int helmp_impl(mlegs_field *s, int power, double alpha, double beta) {
   a.ak = c.d_ak;
   a.napply = power / 2;
   a.combine = 1;
+  a.src = (const cplx *)src;
   a.alpha = alpha;
   a.beta = beta;
   set_del2_ln(&a, s->ln);
@@ -550,8 +553,17 @@ static int lin(int mode, mlegs_field *y, const mlegs_field *x1, const mlegs_fiel
 // svis of fefe/abab/abcn (e.g. ops:1217-1230): returns the un-scaled operator image in `svis` and the factor
 static int viscous_term(const mlegs_field *s, mlegs_field *svis, double *factor, bool *zero) {
   const mlegs_params &p = ctx().p;
-  MLEGS_TRY(copy_data(svis, s));
   *zero = false;
+  if (p.hyperpow != 0 && is_space(s, "FFF")) {
+    // svis = helmp(s) without the copy svis = s: the band operator reads s%e and writes svis%e
+    void *e = svis->e;
+    *svis = *s;
+    svis->e = e;
+    MLEGS_TRY(helmp_impl(svis, p.hyperpow, 0.0, p.visc / hv_signed(), s->e));
+    *factor = hv_signed();
+    return MLEGS_OK;
+  }
+  MLEGS_TRY(copy_data(svis, s));
   if (p.hyperpow == 0) {
     if (p.visc < 5.0e-14) {
       *zero = true;
@@ -614,29 +626,37 @@ int abcn_impl(mlegs_field *s, mlegs_field *s_p, mlegs_field *nl, mlegs_field *nl
   MLEGS_TRY(check_fff(s_p));
   MLEGS_TRY(check_fff(nl_p));
   const mlegs_params &p = ctx().p;
-  mlegs_field sh = temp_like(s, 1);
-  MLEGS_TRY(lin(3, &sh, s, nl, nl_p, dt, 0.0, 0.0));
-  sh.ln = s->ln + dt * (1.5 * nl->ln - 0.5 * nl_p->ln);
+  if (p.hyperpow == 0 && p.visc < 5.0e-14)
+    return fail(MLEGS_E_ARG, "abcn: inviscid case and no linear term in rhs. semi-implicit time adv is impossible");
+  // The reference builds sh = s + dt (1.5 nl - 0.5 nl_p), svis = L s, sh = a (sh + dt/2 svis), solves, and assigns
+  // s = sh (ops:1214-1255).  Here svis is computed first (from the old s), then ONE pass writes a (sh + dt/2 svis)
+  // straight into s%e (same operations in the same order, the intermediate sh rounded to double as the reference
+  // stores it), and the solve runs in place: two field copies and one full pass fewer per call.
+  const double ln_sh = s->ln + dt * (1.5 * nl->ln - 0.5 * nl_p->ln);
   mlegs_field svis = temp_like(s, 2);
   double fac;
   bool zero;
   MLEGS_TRY(viscous_term(s, &svis, &fac, &zero));
-  if (p.hyperpow == 0) {
-    if (p.visc < 5.0e-14)
-      return fail(MLEGS_E_ARG,
-                  "abcn: inviscid case and no linear term in rhs. semi-implicit time adv is impossible");
-    double a = -2.0 / (dt * p.visc);
-    sh.ln = a * (sh.ln + dt / 2.0 * svis.ln);
-    MLEGS_TRY(lin(5, &sh, &svis, nullptr, nullptr, a, dt / 2.0, fac));
-    MLEGS_TRY(ihelm_impl(&sh, a));
-  } else {
-    double a = -2.0 / (dt * hv_signed());
-    double b = p.visc / hv_signed();
-    sh.ln = a * (sh.ln + dt / 2.0 * svis.ln);
-    MLEGS_TRY(lin(5, &sh, &svis, nullptr, nullptr, a, dt / 2.0, fac));
-    MLEGS_TRY(ihelmp_impl(&sh, p.hyperpow, a, b));
+  const double a = (p.hyperpow == 0) ? -2.0 / (dt * p.visc) : -2.0 / (dt * hv_signed());
+  {
+    LinArgs q;
+    q.mode = 9;
+    q.n = nelem(s);
+    q.y = (cplx *)s->e;
+    q.x1 = (const cplx *)nl->e;
+    q.x2 = (const cplx *)nl_p->e;
+    q.x3 = (const cplx *)svis.e;
+    q.a = a;
+    q.b = dt / 2.0;
+    q.c = fac;
+    q.d = dt;
+    MLEGS_TRY(launch_lincomb(q, strm()));
   }
-  MLEGS_TRY(copy_data(s, &sh));
+  s->ln = a * (ln_sh + dt / 2.0 * svis.ln);
+  if (p.hyperpow == 0)
+    MLEGS_TRY(ihelm_impl(s, a));
+  else
+    MLEGS_TRY(ihelmp_impl(s, p.hyperpow, a, p.visc / hv_signed()));
   MLEGS_TRY(copy_data(s_p, s));      // ops:1256: s_p receives the NEW s
   MLEGS_TRY(copy_data(nl_p, nl));
   return MLEGS_OK;
