@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
     int mx = 0;
     for (int kk = 0; kk < KB; ++kk) mx = max(mx, s_reps[kk]);
     s_max = mx;
-    s_any = (mx > 0) || a.combine || (mglob == 0 && k0 == 0 && a.nlnc > 0);
+    s_any = (mx > 0) || a.combine || (mglob == 0 && k0 == 0 && a.nlnc > 0) || a.src != nullptr || a.out_neg;
   }
   __syncthreads();
   if (!s_any) return;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
   for (int kk = 0; kk < KB; ++kk) {
     const int k = k0 + kk;
     if (k >= a.nzl) break;
-    const cplx *col = ((a.combine && a.src) ? a.src : a.e) + ((size_t)k * a.npl + j) * a.nrl;
+    const cplx *col = (a.src ? a.src : a.e) + ((size_t)k * a.npl + j) * a.nrl;
     for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
       cplx v = col[i];
       cur[kk * a.nrl + i] = v;
@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
   }
   __syncthreads();
 
-  const bool direct = (a.napply == 1 && !a.combine && maxreps <= 1 && !lnblk);
+  const bool every_line = a.src != nullptr || a.out_neg;   // out of place / negated: lines the operator leaves alone are written too
+  const bool direct = (a.napply == 1 && !a.combine && maxreps <= 1 && !lnblk && !every_line);
   for (int ap = 0; ap < a.napply; ++ap) {
     for (int r = 0; r < maxreps; ++r) {
       for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
   for (int kk = 0; kk < KB; ++kk) {
     const int k = k0 + kk;
     if (k >= a.nzl) break;
-    if (!a.combine && s_reps[kk] == 0 && !(lnblk && kk == 0)) continue;   // untouched plane
+    if (!a.combine && !every_line && s_reps[kk] == 0 && !(lnblk && kk == 0)) continue;   // untouched plane
     cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
     for (int i = threadIdx.x; i < a.nrl; i += blockDim.x) {
       cplx o = cur[kk * a.nrl + i];
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(1024) band_op_kernel(BandOpArgs a, int KB) {
         cplx q = s2[kk * a.nrl + i], s = s0[kk * a.nrl + i];
         o = make_double2((o.x + a.beta * q.x) + a.alpha * s.x, (o.y + a.beta * q.y) + a.alpha * s.y);
       }
+      if (a.out_neg) o = make_double2(-o.x, -o.y);
       col[i] = o;
     }
   }
@@ -263,7 +265,7 @@ int launch_band_op(const BandOpArgs &a, cudaStream_t st) {
   dim3 grid(a.npl, (a.nzl + KB - 1) / KB);
   int threads = std::min(1024, (a.nrl + 31) / 32 * 32);
   // one pass over the retained lines (helmp's whole-array combination touches every line of the block)
-  const double lines_b = a.combine ? (double)a.nrl * a.npl * a.nzl
+  const double lines_b = (a.combine || a.src || a.out_neg) ? (double)a.nrl * a.npl * a.nzl
                                    : retained_elems(a.nrl, a.npl, a.nzl, 0, a.m0, a.nrc, a.npc, a.nzc, a.nzcu, a.ms);
   prof_begin(a.combine ? "helmp_band" : (a.nb == 3 ? "xxdx_band" : "del2_band"), st, 32.0 * lines_b);
   if (a.nb == 3)

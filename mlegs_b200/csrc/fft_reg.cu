@@ -186,9 +186,10 @@ __device__ __forceinline__ double div_by(double x, double b, double y) {
 
 // MODE: FFT_C2C_FWD / FFT_C2C_BWD / FFT_R2C_FWD / FFT_C2R_BWD (kernels.h).
 // one tile = L lines of one scalar (blockIdx.y); `blk` = tile index
-// EXT: the launch carries a fused exchange and/or fused row scaling (kept out of the plain kernels: the extra state
-// costs them 8-26 registers and a resident CTA per SM)
-template <int MODE, int N, int E, int THREADS, bool EXT>
+// EXT != 0: the launch carries a fused exchange and/or fused row scaling (kept out of the plain kernels: the extra state
+// costs them 8-26 registers and a resident CTA per SM); EXT == 2: c2r whose input columns are in the transit layout of a
+// fused exchange(1,2) (a kernel of its own: the column arithmetic costs the row-scaling kernel 15 %)
+template <int MODE, int N, int E, int THREADS, int EXT>
 __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk) {
   constexpr int T = N / E, L = THREADS / T;
   using S = Sched<N, E>;
@@ -239,7 +240,7 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk)
     // Im(C_0), Im(C_N) are ignored like external/ffte-7.0/zdfft2d.f:119-128 does.
     // column of point m inside the input block (transit layout of a fused exchange: grouped by owner of m)
     auto colof = [&](int m) -> long long {
-      if (EXT && a.rs.perm_p > 1) return (long long)a.rs.perm_off[m % a.rs.perm_p] + m / a.rs.perm_p;
+      if (EXT == 2) return (long long)a.rs.perm_off[m % a.rs.perm_p] + m / a.rs.perm_p;
       return m;
     };
 #pragma unroll
@@ -355,16 +356,16 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk)
 
 // resident CTAs per SM the kernels are compiled for: 5 (4 for c2r) for the plain short-line kernels (48 / 64 registers),
 // 2 for the 16-points-per-thread ones (an explicit 1 lets ptxas take 140-172 registers and halves the occupancy)
-template <int MODE, int N, int THREADS, bool EXT>
+template <int MODE, int N, int THREADS, int EXT>
 struct MinBlocks {
   static constexpr int value =
       THREADS != 256 ? 1 : (N <= 64 ? (EXT ? 3 : (MODE == FFT_C2R_BWD ? 4 : 5)) : 2);
 };
 
-template <int MODE, int N, int E, int THREADS, bool EXT>
+template <int MODE, int N, int E, int THREADS, int EXT>
 __global__ void __launch_bounds__(THREADS, MinBlocks<MODE, N, THREADS, EXT>::value) fft_reg_kernel(FftRegArgs a) {
   if (!EXT) {
-    fft_reg_tile<MODE, N, E, THREADS, false>(a, blockIdx.x);   // one tile per CTA
+    fft_reg_tile<MODE, N, E, THREADS, 0>(a, blockIdx.x);   // one tile per CTA
     return;
   }
   constexpr int L = THREADS / (N / E);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, MinBlocks<MODE, N, THREADS, EXT>::val
   // the fused exchange runs a grid-stride loop so that the system-scope fence that ends it (an NVLink round trip during
   // which the CTA still holds its SM resources) is paid once per CTA, not once per tile
   for (long long blk = blockIdx.x; blk < ntiles; blk += gridDim.x) {
-    fft_reg_tile<MODE, N, E, THREADS, true>(a, blk);
+    fft_reg_tile<MODE, N, E, THREADS, EXT>(a, blk);
     if (blk + gridDim.x < ntiles) __syncthreads();   // the tile's shared buffer is reused
   }
   if (MODE == FFT_R2C_FWD && a.use_peer) dist_finish_put(a.pt, gridDim.x * gridDim.y);
@@ -386,7 +387,7 @@ struct RegCfg {
   static constexpr size_t smem = (size_t)(N + 1) * L * sizeof(cplx);
 };
 
-template <int MODE, int N, int E, int THREADS, bool EXT>
+template <int MODE, int N, int E, int THREADS, int EXT>
 static int launch_one_ext(const FftRegArgs &a, int nfields, cudaStream_t st) {
   using C = RegCfg<N, E, THREADS>;
   static bool attr = false;
@@ -418,9 +419,10 @@ template <int MODE, int N, int E, int THREADS>
 static int launch_one(const FftRegArgs &a, int nfields, cudaStream_t st) {
   // the extended kernel only exists for the real modes (fused exchange: r2c; fused row scaling: r2c and c2r)
   if constexpr (MODE == FFT_R2C_FWD || MODE == FFT_C2R_BWD) {
-    if (a.use_peer || a.rs.mode != 0 || a.rs.perm_p > 1) return launch_one_ext<MODE, N, E, THREADS, true>(a, nfields, st);
+    if (MODE == FFT_C2R_BWD && a.rs.perm_p > 1) return launch_one_ext<MODE, N, E, THREADS, 2>(a, nfields, st);
+    if (a.use_peer || a.rs.mode != 0) return launch_one_ext<MODE, N, E, THREADS, 1>(a, nfields, st);
   }
-  return launch_one_ext<MODE, N, E, THREADS, false>(a, nfields, st);
+  return launch_one_ext<MODE, N, E, THREADS, 0>(a, nfields, st);
 }
 
 template <int MODE>

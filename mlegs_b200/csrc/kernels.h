@@ -190,7 +190,9 @@ int launch_tv_combine(const TvCombineArgs &a, cudaStream_t st);
 // ---- banded.cu --------------------------------------------------------------------------
 struct BandOpArgs {
   cplx *e;
-  const cplx *src = nullptr;   // helmp only (combine != 0): planes are read from here instead of e (replaces a field copy)
+  const cplx *src = nullptr;   // != nullptr: planes are read from here and EVERY line of the block is written to e
+                               // (operator image where the operator acts, a copy elsewhere): replaces a field copy
+  int out_neg = 0;             // the whole result is negated on the way out (the `s%e = -s%e` after del2, ops:1489, 1554)
   int nrl, npl, nzl, m0;
   int ms = 1;            // column j holds m = m0 + j ms
   const double *tab;     // (ne, nb, npchop) band coefficients

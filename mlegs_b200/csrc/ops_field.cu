@@ -314,12 +314,18 @@ static int band_args(const mlegs_field *s, BandOpArgs *a) {
   return MLEGS_OK;
 }
 
-int xxdx_impl(mlegs_field *s) {
+// src != nullptr (xxdx, del2): the operand is read from there (same layout and metadata as s) and the result written to
+// s%e -- `t = s; call op(t)` without the copy.  negate: the whole result is negated on the way out.
+int xxdx_impl(mlegs_field *s, const void *src = nullptr);
+int del2_impl(mlegs_field *s, bool horizontal, const void *src = nullptr, bool negate = false);
+
+int xxdx_impl(mlegs_field *s, const void *src) {
   MLEGS_TRY(ready());
   Context &c = ctx();
-  MLEGS_TRY(require_fff(s));
+  if (!src) MLEGS_TRY(require_fff(s));
   BandOpArgs a;
   MLEGS_TRY(band_args(s, &a));
+  a.src = (const cplx *)src;
   a.tab = c.d_xxdx;
   a.nb = 3;
   a.ak = nullptr;
@@ -342,12 +348,14 @@ static void set_del2_ln(BandOpArgs *a, double ln) {
   a->lnc[2] = cf[2] * ln;
 }
 
-int del2_impl(mlegs_field *s, bool horizontal) {
+int del2_impl(mlegs_field *s, bool horizontal, const void *src, bool negate) {
   MLEGS_TRY(ready());
   Context &c = ctx();
-  MLEGS_TRY(require_fff(s));
+  if (!src) MLEGS_TRY(require_fff(s));
   BandOpArgs a;
   MLEGS_TRY(band_args(s, &a));
+  a.src = (const cplx *)src;
+  a.out_neg = negate ? 1 : 0;
   a.tab = c.d_del2h;
   a.nb = 5;
   a.ak = horizontal ? nullptr : c.d_ak;
@@ -748,23 +756,29 @@ int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr,
   if (!is_space(vr, "PPP")) return fail(MLEGS_E_ARG, "vector_projection: vr must be in PPP");
   if (!is_space(vp, "PPP")) return fail(MLEGS_E_ARG, "vector_projection: vp must be in PPP");
   if (!is_space(vz, "PPP")) return fail(MLEGS_E_ARG, "vector_projection: vz must be in PPP");
-  // ur = chi, up = psi, uz = chi with nrchop offset 3 (ops:1479-1481); they live in the output buffers
-  MLEGS_TRY(copy_data(vr, chi));
-  MLEGS_TRY(copy_data(vp, psi));
-  MLEGS_TRY(copy_data(vz, chi));
+  // ur = chi, up = psi, uz = chi with nrchop offset 3 (ops:1479-1481); they live in the output buffers.  The copies
+  // are not made: the operators below read chi / psi and write into the output buffers (metadata copied here).
+  auto take_meta = [](mlegs_field *dst, const mlegs_field *src) {
+    void *e = dst->e;
+    *dst = *src;
+    dst->e = e;
+  };
+  take_meta(vr, chi);
+  take_meta(vp, psi);
+  take_meta(vz, chi);
   mlegs_field *ur = vr, *up = vp, *uz = vz;
   ur->nrchop_offset = up->nrchop_offset = uz->nrchop_offset = 3;
   ur->npchop_offset = up->npchop_offset = uz->npchop_offset = 0;
   ur->nzchop_offset = up->nzchop_offset = uz->nzchop_offset = 0;
   ChopIdx ci;
   MLEGS_TRY(chop_index(ur, &ci));
-  MLEGS_TRY(xxdx_impl(ur));
-  MLEGS_TRY(xxdx_impl(up));
+  MLEGS_TRY(xxdx_impl(ur, chi->e));
+  MLEGS_TRY(xxdx_impl(up, psi->e));
   TvCombineArgs t;
   t.ur = (cplx *)ur->e;
   t.up = (cplx *)up->e;
   t.psi = (const cplx *)psi->e;
-  t.uz = (const cplx *)uz->e;
+  t.uz = (const cplx *)chi->e;               // uz still equals chi at this point (ops:1481, 1494)
   t.nrl = ur->loc_sz[0];
   t.npl = ur->loc_sz[1];
   t.nzl = ur->loc_sz[2];
@@ -779,8 +793,7 @@ int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr,
   ur->nrchop_offset = up->nrchop_offset = 0;
   MLEGS_TRY(chop_impl(ur));
   MLEGS_TRY(chop_impl(up));
-  MLEGS_TRY(del2_impl(uz, true));
-  MLEGS_TRY(lin(4, uz, nullptr, nullptr, nullptr, -1.0, 0.0, 0.0));
+  MLEGS_TRY(del2_impl(uz, true, chi->e, true));      // uz = -del2h(chi) (ops:1488-1489), one pass
   uz->nrchop_offset = 0;
   MLEGS_TRY(chop_impl(uz));
   // the three backward transforms (ops:1503-1505, 1541) are independent: one launch per stage for all of them
@@ -791,11 +804,13 @@ int tp2vec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *vr,
 
 int tp2curlvec_impl(const mlegs_field *psi, const mlegs_field *chi, mlegs_field *wr, mlegs_field *wp, mlegs_field *wz) {
   MLEGS_TRY(ready());
-  mlegs_field mdel2chi = temp_like(chi, 3);
-  MLEGS_TRY(copy_data(&mdel2chi, chi));
-  set_space3(&mdel2chi, "FFF");
-  MLEGS_TRY(del2_impl(&mdel2chi, false));
-  MLEGS_TRY(lin(4, &mdel2chi, nullptr, nullptr, nullptr, -1.0, 0.0, 0.0));
+  mlegs_field mdel2chi = temp_like(chi, 3);           // metadata of chi, data in a scratch buffer
+  if (is_space(chi, "FFF")) {
+    MLEGS_TRY(del2_impl(&mdel2chi, false, chi->e, true));   // -del2(chi) (ops:1553-1554) without the copy, one pass
+  } else {                                            // del2 transforms its operand first (ops:531-535)
+    MLEGS_TRY(copy_data(&mdel2chi, chi));
+    MLEGS_TRY(del2_impl(&mdel2chi, false, nullptr, true));
+  }
   return tp2vec_impl(&mdel2chi, psi, wr, wp, wz);
 }
 
