@@ -356,14 +356,14 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk)
 
 // resident CTAs per SM the kernels are compiled for: 5 (4 for c2r) for the plain short-line kernels (48 / 64 registers),
 // 2 for the 16-points-per-thread ones (an explicit 1 lets ptxas take 140-172 registers and halves the occupancy)
-template <int MODE, int N, int THREADS, int EXT>
+template <int MODE, int N, int E, int THREADS, int EXT>
 struct MinBlocks {
   static constexpr int value =
-      THREADS != 256 ? 1 : (N <= 64 ? (EXT ? 3 : (MODE == FFT_C2R_BWD ? 4 : 5)) : 2);
+      THREADS != 256 ? 1 : (E <= 8 ? (EXT ? 3 : (MODE == FFT_C2R_BWD ? 4 : 5)) : 2);
 };
 
 template <int MODE, int N, int E, int THREADS, int EXT>
-__global__ void __launch_bounds__(THREADS, MinBlocks<MODE, N, THREADS, EXT>::value) fft_reg_kernel(FftRegArgs a) {
+__global__ void __launch_bounds__(THREADS, MinBlocks<MODE, N, E, THREADS, EXT>::value) fft_reg_kernel(FftRegArgs a) {
   if (!EXT) {
     fft_reg_tile<MODE, N, E, THREADS, 0>(a, blockIdx.x);   // one tile per CTA
     return;
@@ -430,7 +430,11 @@ static int launch_mode(int n, const FftRegArgs &a, int nfields, cudaStream_t st)
   switch (n) {
     case 32: return launch_one<MODE, 32, 8, 256>(a, nfields, st);
     case 64: return launch_one<MODE, 64, 8, 256>(a, nfields, st);
-    case 128: return launch_one<MODE, 128, 16, 256>(a, nfields, st);
+    case 128: {
+      static const bool e8 = getenv("MLEGS_FFT_E8") != nullptr;   // A/B: 8 points per thread, three passes, 4-5 CTAs per SM
+      if (e8) return launch_one<MODE, 128, 8, 256>(a, nfields, st);
+      return launch_one<MODE, 128, 16, 256>(a, nfields, st);
+    }
     case 256: return launch_one<MODE, 256, 16, 256>(a, nfields, st);
     case 512: return launch_one<MODE, 512, 16, 256>(a, nfields, st);   // 8 lines per CTA, 3 CTAs per SM: 0.87 -> 0.78 ms at 512^3
     case 1024: return launch_one<MODE, 1024, 16, 512>(a, nfields, st);

@@ -476,3 +476,83 @@ def test_fftreat(case):
     mb.fftreat(s)
     mo.fftreat(so, ok)
     assert rel_l2(s.download(), so.e) < TOL, (case, "chop offset")
+
+
+def test_scalar_transport_2d_steps():
+    """BASELINE.json configs[0]: the 2-D tutorial time integration (src/apps/scalar_transport_2d.f90:139-176 with the
+    input_2d.params values of tools/validate_tutorials.py:255-269: NR=32, NP=48, NZ=1, NRCHOP=32, NPCHOP=25, ELL=1,
+    VISC=5e-3, DT=1e-2).  The app's own array statements (ds/dphi = i m s, the swirl velocity, the source term,
+    :221-268) run on the host for both sides, exactly as the Fortran app writes them on s%e; every library call
+    (trans, febe, calcat0) goes through the C ABI on the device and through the oracle, step by step."""
+    kit, ok = _setup("gate2d")
+    p = kit.params
+    nr, nph = p.nr, p.np // 2
+    dt = 1.0e-2
+    r = ok.r
+    pang = np.array([2.0 * mo.PI / p.np * i for i in range(p.np)])
+    swirl = (1.0 - np.exp(-r) ** 2.0) / r ** 2.0
+
+    def source(t):
+        src = np.zeros(ok.glb_sz, dtype=np.complex128, order="F")
+        xo = yo = 0.5
+        pr, pi_ = pang[0::2][None, :], pang[1::2][None, :]
+        rr = np.sqrt((r[:, None] * np.cos(pr) - xo) ** 2.0 + (r[:, None] * np.sin(pr) - yo) ** 2.0)
+        ri = np.sqrt((r[:, None] * np.cos(pi_) - xo) ** 2.0 + (r[:, None] * np.sin(pi_) - yo) ** 2.0)
+        val = (np.maximum(1.0 - (4 * rr) ** 8.0, 0.0) + 1j * np.maximum(1.0 - (4 * ri) ** 8.0, 0.0)) / 2.0
+        src[:nr, :nph, 0] = val * (1.0 - np.cos(mo.PI * t))
+        return src
+
+    class Dev:
+        def __init__(self):
+            self.s = mb.Scalar("PPP").upload(np.zeros(ok.glb_sz, dtype=np.complex128, order="F"))
+
+        def rhs(self, t):
+            nls = self.s.copy()
+            mb.trans(nls, "FFF")
+            e = nls.download()
+            e[:, :p.npchop, :] *= 1j * np.arange(p.npchop)[None, :, None]      # ds/dphi, columns m < chopp
+            nls.upload(e)
+            mb.trans(nls, "PPP")
+            e = nls.download()
+            e[:nr] = -e[:nr] * swirl[:, None, None]
+            nls.upload(np.asfortranarray(-e + source(t)))
+            return nls
+
+        def step(self, t):
+            nls = self.rhs(t)
+            mb.trans(self.s, "FFF")
+            mb.trans(nls, "FFF")
+            mb.febe(self.s, nls, dt)
+            mb.trans(self.s, "PPP")
+            return self.s.download(), mb.calcat0(self.s)[0]
+
+    class Ora:
+        def __init__(self):
+            self.s = mo.Scalar(e=np.zeros(ok.glb_sz, dtype=np.complex128, order="F"), space="PPP")
+
+        def rhs(self, t):
+            nls = self.s.copy()
+            mo.trans(nls, "FFF", ok)
+            nls.e[:, :p.npchop, :] *= 1j * np.arange(p.npchop)[None, :, None]
+            mo.trans(nls, "PPP", ok)
+            nls.e[:nr] = -nls.e[:nr] * swirl[:, None, None]
+            nls.e = np.asfortranarray(-nls.e + source(t))
+            return nls
+
+        def step(self, t):
+            nls = self.rhs(t)
+            mo.trans(self.s, "FFF", ok)
+            mo.trans(nls, "FFF", ok)
+            mo.febe(self.s, nls, dt, ok)
+            mo.trans(self.s, "PPP", ok)
+            return self.s.e.copy(), mo.calcat0(self.s, ok)[0]
+
+    dev, ora = Dev(), Ora()
+    t = 0.0
+    for n in range(4):
+        t += dt
+        got, g0 = dev.step(t)
+        want, w0 = ora.step(t)
+        assert np.linalg.norm(want) > 0.0
+        assert rel_l2(got, want) < TOL, (n, rel_l2(got, want))
+        assert abs(g0 - w0) <= TOL * max(1.0, abs(w0)), (n, g0, w0)

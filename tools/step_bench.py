@@ -20,6 +20,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=128)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--ncu-step", action="store_true",
+                help="bracket ONE extra step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
 args = ap.parse_args()
 
 import torch  # noqa: E402
@@ -67,6 +69,12 @@ if dist is not None:
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+if args.ncu_step:
+    mb.device_sync()
+    torch.cuda.cudart().cudaProfilerStart()
+    vortex.step(st, dt, check=False)
+    mb.device_sync()
+    torch.cuda.cudart().cudaProfilerStop()
 mb.prof_enable(True)
 vortex.step(st, dt)
 prof = mb.prof_report()
