@@ -250,7 +250,9 @@ int launch_band_op(const BandOpArgs &a, cudaStream_t st) {
   if (a.npl <= 0 || a.nzl <= 0) return MLEGS_OK;
   const int nbuf = a.combine ? 4 : 2;
   int KB = BAND_KB_MAX;
-  while (KB > 1 && (size_t)nbuf * KB * a.nrl * sizeof(cplx) > 72 * 1024) KB >>= 1;
+  static const char *cap_env = getenv("MLEGS_BAND_SMEM_KB");   // A/B: shared memory per CTA (planes per CTA vs CTAs per SM)
+  const size_t cap = (size_t)(cap_env ? atoi(cap_env) : 36) * 1024;   // 256^3: xxdx 0.43 -> 0.31 ms, del2 0.35 -> 0.31 (72 -> 36 KB)
+  while (KB > 1 && (size_t)nbuf * KB * a.nrl * sizeof(cplx) > cap) KB >>= 1;
   size_t smem = (size_t)nbuf * KB * a.nrl * sizeof(cplx);
   if (smem > 220 * 1024) return fail(MLEGS_E_ARG, "band operator: radial size too large for shared memory");
   static size_t attr_set3 = 0, attr_set5 = 0;
@@ -672,6 +674,176 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
   }
 }
 
+// Narrow bands (ihelm, idel2: kl <= 3, kl + ku <= 5): the wide kernel above keeps 3 of 32 lanes busy in the forward
+// sweep and 5 in the back substitution, and its throughput is set by the latency of one dependent column step per
+// warp.  Here a warp carries FOUR systems, eight lanes each: lane g of a group owns the multiplier L(g) (forward) /
+// the entry U(jj - g, jj) (backward) of its system, fetched 8 columns ahead of the dependent chain; same operations in
+// the same order per system as the wide kernel (and as zgbtrs / ztbsv), so results are bit-identical.
+// The same with 16 lanes per system (two systems per warp) serves the hyperviscous operators (kl = ku <= 8): the back
+// substitution's bandwidth kl + ku = 16 is one more than a group has lanes, so lane 0 of a group also carries the
+// entry at distance 16 (template parameter G = lanes per system).
+#define NSOLVE_WARPS 4
+template <bool MIRROR, int NSOLVE_GROUP>
+__global__ void __launch_bounds__(NSOLVE_WARPS * 32) band_solve_cached_narrow_kernel(SolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int SPW = 32 / NSOLVE_GROUP;            // systems per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / NSOLVE_GROUP, gl = lane % NSOLVE_GROUP, gbase = grp * NSOLVE_GROUP;
+  const int nsys = a.npl * a.nk;
+  const int kl = a.kl, ku = a.ku, kv = kl + ku, ldab = 2 * kl + ku + 1;
+  double *rhs = reinterpret_cast<double *>(smraw) + (size_t)(warp * SPW + grp) * 2 * a.nnmax;
+  const int per_block = NSOLVE_WARPS * SPW;
+  for (int sys0 = blockIdx.x * per_block + warp * SPW; sys0 < nsys; sys0 += gridDim.x * per_block) {
+    const int sys = sys0 + grp;
+    const bool have = sys < nsys;
+    const int j = have ? sys / a.nk : 0;
+    const int kf = a.k0 + (have ? sys % a.nk : 0);
+    const int mglob = a.m0 + j * a.ms;
+    const int nn = have ? nn_of(mglob, a.nrc, a.npc) : 0;
+    // loop bounds are warp-uniform: the longest system of the warp (its groups share a column except at column ends)
+    int nnw = nn;
+#pragma unroll
+    for (int off = NSOLVE_GROUP; off < 32; off <<= 1) nnw = max(nnw, __shfl_xor_sync(0xffffffffu, nnw, off));
+    const long long c0 = have ? a.fac_off[j] + (long long)(kf - a.k0) * nn : 0;
+    const double *__restrict__ AB = a.fac_ab + c0 * ldab;
+    const unsigned char *__restrict__ piv = a.fac_piv + c0;
+    for (int pass = 0; pass < (MIRROR ? 2 : 1); ++pass) {
+      if (MIRROR && pass == 0 && a.mirror_mode == 2) continue;
+      const int k = (!MIRROR || pass == 0) ? kf : a.mirror_nz - kf;
+      // a group whose mirrored plane does not exist sits this pass out (nnp = 0); the warp stays together
+      const bool live = nn > 0 && !(MIRROR && pass == 1 && (kf == 0 || k < a.mirror_lo || k >= a.mirror_nz));
+      const int nnp = live ? nn : 0;
+      cplx *col = a.e + ((size_t)(live ? k : 0) * a.npl + j) * a.nrl;
+      const bool special = (pass == 0 && a.special00 && mglob == 0 && k == 0 && live);
+      for (int i = gl; i < nnp; i += NSOLVE_GROUP) {
+        cplx v;
+        if (special && a.special00 == 2)
+          v = (i == 0) ? make_double2(a.preln_rhs, 0.0) : col[i - 1];
+        else
+          v = col[i];
+        rhs[2 * i] = v.x;
+        rhs[2 * i + 1] = v.y;
+      }
+      __syncwarp();
+      // ---- forward sweep (zgbtrs, external/lapack/SRC/zgbtrs.f:205-232) ----
+      {
+        double lcur[8], lnxt[8];
+        int pcur[8], pnxt[8];
+        auto loadL = [&](int jb, double(&l)[8], int(&pv)[8]) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int cc = jb + u;
+            l[u] = (cc < nnp && gl >= 1 && gl <= kl) ? __ldg(&AB[(size_t)cc * ldab + kv + gl]) : 0.0;
+            pv[u] = (cc < nnp && gl == 0) ? (int)__ldg(&piv[cc]) : 0;
+          }
+        };
+        loadL(0, lcur, pcur);
+        for (int jb = 0; jb < nnw; jb += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            lnxt[u] = 0.0;
+            pnxt[u] = 0;
+          }
+          if (jb + 8 < nnw) loadL(jb + 8, lnxt, pnxt);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int jj = jb + u;
+            if (jj >= nnw) break;
+            const bool on = jj < nnp;
+            const int km = on ? min(kl, nnp - 1 - jj) : 0;
+            const int jp = __shfl_sync(0xffffffffu, pcur[u], gbase);
+            if (on && jp != 0 && gl == 0) {
+              double tr = rhs[2 * (jj + jp)], ti = rhs[2 * (jj + jp) + 1];
+              rhs[2 * (jj + jp)] = rhs[2 * jj];
+              rhs[2 * (jj + jp) + 1] = rhs[2 * jj + 1];
+              rhs[2 * jj] = tr;
+              rhs[2 * jj + 1] = ti;
+            }
+            __syncwarp();
+            if (gl >= 1 && gl <= km) {
+              const double l = lcur[u];
+              double tr = -rhs[2 * jj], ti = -rhs[2 * jj + 1];
+              rhs[2 * (jj + gl)] = rhs[2 * (jj + gl)] + l * tr;
+              rhs[2 * (jj + gl) + 1] = rhs[2 * (jj + gl) + 1] + l * ti;
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            lcur[u] = lnxt[u];
+            pcur[u] = pnxt[u];
+          }
+        }
+      }
+      // ---- ztbsv: upper, no transpose, non-unit, bandwidth kv; the systems of a warp run bottom-aligned ----
+      {
+        double ucur[8], unxt[8];
+        double vcur[8], vnxt[8];                     // entry at distance gl + G (only when kv >= G: G = 16, kv = 16)
+        const int g2 = gl + NSOLVE_GROUP;
+        const bool second = NSOLVE_GROUP == 16 && g2 <= kv;
+        auto loadU = [&](int jtop, double(&u)[8], double(&v)[8]) {
+#pragma unroll
+          for (int sidx = 0; sidx < 8; ++sidx) {
+            const int cc = jtop - sidx;
+            u[sidx] = (cc >= 0 && cc < nnp && gl <= kv && gl <= cc) ? __ldg(&AB[(size_t)cc * ldab + kv - gl]) : 0.0;
+            if (NSOLVE_GROUP == 16)
+              v[sidx] = (second && cc >= 0 && cc < nnp && g2 <= cc) ? __ldg(&AB[(size_t)cc * ldab + kv - g2]) : 0.0;
+          }
+        };
+        loadU(nnw - 1, ucur, vcur);
+        for (int jt = nnw - 1; jt >= 0; jt -= 8) {
+#pragma unroll
+          for (int sidx = 0; sidx < 8; ++sidx) unxt[sidx] = vnxt[sidx] = 0.0;
+          if (jt - 8 >= 0) loadU(jt - 8, unxt, vnxt);
+#pragma unroll
+          for (int sidx = 0; sidx < 8; ++sidx) {
+            const int jj = jt - sidx;
+            if (jj < 0) break;
+            const double u = ucur[sidx];
+            const double ujj = __shfl_sync(0xffffffffu, u, gbase);
+            double xr = 0.0, xi = 0.0;
+            if (jj < nnp) {
+              xr = rhs[2 * jj];
+              xi = rhs[2 * jj + 1];
+            }
+            const bool act = jj < nnp && (xr != 0.0 || xi != 0.0);
+            if (act) {
+              xr = xr / ujj;
+              xi = xi / ujj;
+            }
+            __syncwarp();
+            if (act) {
+              if (gl == 0) {
+                rhs[2 * jj] = xr;
+                rhs[2 * jj + 1] = xi;
+              }
+              const int cnt = min(jj, kv);
+              if (gl >= 1 && gl <= cnt) {
+                const int i = jj - gl;
+                rhs[2 * i] = rhs[2 * i] - xr * u;
+                rhs[2 * i + 1] = rhs[2 * i + 1] - xi * u;
+              }
+              if (NSOLVE_GROUP == 16 && second && g2 <= cnt) {
+                const int i = jj - g2;
+                rhs[2 * i] = rhs[2 * i] - xr * vcur[sidx];
+                rhs[2 * i + 1] = rhs[2 * i + 1] - xi * vcur[sidx];
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int sidx = 0; sidx < 8; ++sidx) {
+            ucur[sidx] = unxt[sidx];
+            vcur[sidx] = vnxt[sidx];
+          }
+        }
+      }
+      for (int i = gl; i < nnp; i += NSOLVE_GROUP) col[i] = make_double2(rhs[2 * i], rhs[2 * i + 1]);
+      __syncwarp();
+    }   // pass
+  }
+}
+
 // ---- factor cache ---------------------------------------------------------------------------------------------
 struct FactorEntry {
   SolveArgs key;            // operator identity (pointer fields zeroed)
@@ -804,7 +976,33 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
     const double rhs_cols = a.mirror_mode == 1 ? 2.0 * syscols : syscols;
     prof_begin(a.power > 2 ? "ihelmp_solve_cached" : "band_solve_cached", st,
                syscols * (ldab * 8.0 + 1.0) + 32.0 * rhs_cols);
-    if (a.mirror_mode != 0)
+    static const bool no_narrow = getenv("MLEGS_SOLVE_WIDE") != nullptr;   // A/B timing
+    const int gsz = (a.kl <= 3 && a.kl + a.ku <= 5) ? 8 : ((a.kl <= 8 && a.kl + a.ku <= 16) ? 16 : 0);
+    if (gsz && !no_narrow) {
+      // several systems per warp: 8 lanes each for the narrow bands, 16 for the hyperviscous operators
+      const int spw = 32 / gsz;
+      const size_t nsmem = (size_t)NSOLVE_WARPS * spw * 2 * a.nnmax * sizeof(double);
+      static size_t nattr = 0;
+      if (nsmem > 48 * 1024 && nsmem > nattr) {
+        CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+        CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+        CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+        CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
+        nattr = nsmem;
+      }
+      const int nblocks = (nsys + NSOLVE_WARPS * spw - 1) / (NSOLVE_WARPS * spw);
+      if (gsz == 8) {
+        if (a.mirror_mode != 0)
+          band_solve_cached_narrow_kernel<true, 8><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
+        else
+          band_solve_cached_narrow_kernel<false, 8><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
+      } else {
+        if (a.mirror_mode != 0)
+          band_solve_cached_narrow_kernel<true, 16><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
+        else
+          band_solve_cached_narrow_kernel<false, 16><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
+      }
+    } else if (a.mirror_mode != 0)
       band_solve_cached_kernel<true><<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
     else
       band_solve_cached_kernel<false><<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);

@@ -22,26 +22,28 @@ static inline unsigned ew_grid(size_t n) {
 // masks: chop (ops:6-41) and dealias (ops:43-70)
 // ---------------------------------------------------------------------------------------------
 
-__global__ void mask_kernel(MaskArgs a) {
-  const size_t n = (size_t)a.nrl * a.npl * a.nzl;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    int i = (int)(idx % a.nrl);
-    size_t t = idx / a.nrl;
-    int j = (int)(t % a.npl);
-    int k = (int)(t / a.npl);
-    int m = a.m0 + j * a.ms;
-    bool z = false;
-    if (a.row_mode) {
+// One warp per (column, plane) line: the line is zeroed as a whole (column beyond the azimuthal cut, plane inside the
+// axial cut) or from its truncation row on; retained entries are never read or written.
+__global__ void __launch_bounds__(EW_THREADS) mask_kernel(MaskArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long nlines = (long long)a.npl * a.nzl;
+  const long long wstride = (long long)gridDim.x * (EW_THREADS / 32);
+  for (long long line = (long long)blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5); line < nlines; line += wstride) {
+    const int j = (int)(line % a.npl), k = (int)(line / a.npl);
+    const int m = a.m0 + j * a.ms;
+    int first = a.nrl;                                 // first zeroed row of this line
+    if (m >= a.col_cut || (k >= a.kz_lo && k < a.kz_hi)) {
+      first = 0;
+    } else if (a.row_mode) {
       int nn = 0;
       if (m < a.npc_rows) {
         nn = min(a.nrc, a.nrc - m);
         nn = nn > 0 ? nn : 0;
       }
-      z = z || (a.r0 + i >= nn);
+      first = min(max(nn - a.r0, 0), a.nrl);
     }
-    z = z || (m >= a.col_cut);
-    z = z || (k >= a.kz_lo && k < a.kz_hi);
-    if (z) a.e[idx] = make_double2(0.0, 0.0);
+    cplx *col = a.e + (size_t)line * a.nrl;
+    for (int i = first + lane; i < a.nrl; i += 32) col[i] = make_double2(0.0, 0.0);
   }
 }
 
@@ -68,7 +70,7 @@ int launch_mask(const MaskArgs &a, cudaStream_t st) {
     }
   }
   prof_begin("mask", st, 16.0 * zeroed);
-  mask_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(a);
+  mask_kernel<<<ew_grid((size_t)a.npl * a.nzl * 32), EW_THREADS, 0, st>>>(a);
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;

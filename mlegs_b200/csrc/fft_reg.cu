@@ -430,14 +430,10 @@ static int launch_mode(int n, const FftRegArgs &a, int nfields, cudaStream_t st)
   switch (n) {
     case 32: return launch_one<MODE, 32, 8, 256>(a, nfields, st);
     case 64: return launch_one<MODE, 64, 8, 256>(a, nfields, st);
-    case 128: {
-      static const bool e8 = getenv("MLEGS_FFT_E8") != nullptr;   // A/B: 8 points per thread, three passes, 4-5 CTAs per SM
-      if (e8) return launch_one<MODE, 128, 8, 256>(a, nfields, st);
-      return launch_one<MODE, 128, 16, 256>(a, nfields, st);
-    }
+    case 128: return launch_one<MODE, 128, 16, 256>(a, nfields, st);   // (8 points per thread, 3 passes: 51 vs 46 us at 128^3)
     case 256: return launch_one<MODE, 256, 16, 256>(a, nfields, st);
     case 512: return launch_one<MODE, 512, 16, 256>(a, nfields, st);   // 8 lines per CTA, 3 CTAs per SM: 0.87 -> 0.78 ms at 512^3
-    case 1024: return launch_one<MODE, 1024, 16, 512>(a, nfields, st);
+    case 1024: return launch_one<MODE, 1024, 16, 512>(a, nfields, st);   // (4 lines per CTA, 3 CTAs per SM: 482 vs 489 us)
   }
   return fail(MLEGS_E_ARG, "fft_reg: unsupported length");
 }
