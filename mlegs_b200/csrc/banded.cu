@@ -679,9 +679,8 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
 // warp.  Here a warp carries FOUR systems, eight lanes each: lane g of a group owns the multiplier L(g) (forward) /
 // the entry U(jj - g, jj) (backward) of its system, fetched 8 columns ahead of the dependent chain; same operations in
 // the same order per system as the wide kernel (and as zgbtrs / ztbsv), so results are bit-identical.
-// The same with 16 lanes per system (two systems per warp) serves the hyperviscous operators (kl = ku <= 8): the back
-// substitution's bandwidth kl + ku = 16 is one more than a group has lanes, so lane 0 of a group also carries the
-// entry at distance 16 (template parameter G = lanes per system).
+// (Template parameter: lanes per system.  A 16-lane form for the hyperviscous operators, kl = ku <= 8 with lane 0 also
+// carrying the entry at distance 16 of the back substitution, was measured slower than the wide kernel.)
 #define NSOLVE_WARPS 4
 template <bool MIRROR, int NSOLVE_GROUP>
 __global__ void __launch_bounds__(NSOLVE_WARPS * 32) band_solve_cached_narrow_kernel(SolveArgs a) {
@@ -977,31 +976,25 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
     prof_begin(a.power > 2 ? "ihelmp_solve_cached" : "band_solve_cached", st,
                syscols * (ldab * 8.0 + 1.0) + 32.0 * rhs_cols);
     static const bool no_narrow = getenv("MLEGS_SOLVE_WIDE") != nullptr;   // A/B timing
-    const int gsz = (a.kl <= 3 && a.kl + a.ku <= 5) ? 8 : ((a.kl <= 8 && a.kl + a.ku <= 16) ? 16 : 0);
+    // Several systems per warp pay when there are more systems than the wide kernel keeps resident (256^3: ihelm / idel2
+    // 0.56 -> 0.45 ms); with fewer, the latency of one system decides and the wide kernel is faster (128^3: 0.095 vs
+    // 0.13 ms).  The 16-lane form for the hyperviscous operators lost at every size (256^3: 1.30 vs 1.21 ms) and is not
+    // dispatched.
+    const int gsz = (a.kl <= 3 && a.kl + a.ku <= 5 && nsys >= 16384) ? 8 : 0;
     if (gsz && !no_narrow) {
-      // several systems per warp: 8 lanes each for the narrow bands, 16 for the hyperviscous operators
       const int spw = 32 / gsz;
       const size_t nsmem = (size_t)NSOLVE_WARPS * spw * 2 * a.nnmax * sizeof(double);
       static size_t nattr = 0;
       if (nsmem > 48 * 1024 && nsmem > nattr) {
         CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
         CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
-        CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
-        CUDA_TRY(cudaFuncSetAttribute(band_solve_cached_narrow_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsmem));
         nattr = nsmem;
       }
       const int nblocks = (nsys + NSOLVE_WARPS * spw - 1) / (NSOLVE_WARPS * spw);
-      if (gsz == 8) {
-        if (a.mirror_mode != 0)
-          band_solve_cached_narrow_kernel<true, 8><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
-        else
-          band_solve_cached_narrow_kernel<false, 8><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
-      } else {
-        if (a.mirror_mode != 0)
-          band_solve_cached_narrow_kernel<true, 16><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
-        else
-          band_solve_cached_narrow_kernel<false, 16><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
-      }
+      if (a.mirror_mode != 0)
+        band_solve_cached_narrow_kernel<true, 8><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
+      else
+        band_solve_cached_narrow_kernel<false, 8><<<nblocks, NSOLVE_WARPS * 32, nsmem, st>>>(a);
     } else if (a.mirror_mode != 0)
       band_solve_cached_kernel<true><<<blocks, CSOLVE_WARPS * 32, smem, st>>>(a);
     else
