@@ -564,9 +564,11 @@ int mlegs_b200_trans_host_batch(int n, void *const *host_e, const char from[3], 
   }
   // group size: what one exchange epoch carries, within 6 GB of staging memory, at most a third of the batch so that
   // the three-deep pipeline has something to overlap
-  // One rank: PCIe is the bottleneck and small groups pipeline best (an eighth of the batch).  Several ranks: a group
-  // shares one exchange + barrier, so it is as large as an epoch carries while leaving three groups to overlap.
-  int group = c.nranks > 1 ? std::min({MLEGS_MAXB, dist_window_batch(), (n + NB - 1) / NB}) : std::min(MLEGS_MAXB, n / 8);
+  // One rank: PCIe is the bottleneck (the transforms of a field take a sixth of its two copies), so the pipeline runs
+  // one field at a time and its fill and drain cost one field each (2.15 -> 2.5 GDOF/s at 128^3 against groups of 2).
+  // Several ranks: a group shares one exchange + barrier, so it is as large as an epoch carries while leaving three
+  // groups to overlap.
+  int group = c.nranks > 1 ? std::min({MLEGS_MAXB, dist_window_batch(), (n + NB - 1) / NB}) : 1;
   group = (int)std::max<size_t>(1, std::min<size_t>(std::max(group, 1), ((size_t)6 << 30) / (NB * c.field_bytes)));
   if (f_bytes != c.field_bytes || f_group < group) {
     CUDA_TRY(cudaStreamSynchronize(s_in));
