@@ -429,8 +429,11 @@ template <int MODE>
 static int launch_mode(int n, const FftRegArgs &a, int nfields, cudaStream_t st) {
   switch (n) {
     case 32: return launch_one<MODE, 32, 8, 256>(a, nfields, st);
+    // measured at 128^3 (profiles/r2/README.md): 8 points per thread and 3 passes for N = 128: 51 vs 46 us; 128-thread CTAs
+    // (16 lines each, twice as many per SM) for N = 64 / 128: 58 / 47 vs 60 / 47 us -- occupancy is not what holds these
+    // kernels at 0.66-0.74 of the copy bandwidth
     case 64: return launch_one<MODE, 64, 8, 256>(a, nfields, st);
-    case 128: return launch_one<MODE, 128, 16, 256>(a, nfields, st);   // (8 points per thread, 3 passes: 51 vs 46 us at 128^3)
+    case 128: return launch_one<MODE, 128, 16, 256>(a, nfields, st);
     case 256: return launch_one<MODE, 256, 16, 256>(a, nfields, st);
     case 512: return launch_one<MODE, 512, 16, 256>(a, nfields, st);   // 8 lines per CTA, 3 CTAs per SM: 0.87 -> 0.78 ms at 512^3
     case 1024: return launch_one<MODE, 1024, 16, 512>(a, nfields, st);   // (4 lines per CTA, 3 CTAs per SM: 482 vs 489 us)
