@@ -638,31 +638,21 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
       }
       // thread holds C[row = tile*8 + lane/4][cols 2*(lane%4), +1] of each 8x8 tile == one complex per parity: rows n, n+1
       // of one z plane (32 contiguous bytes).  The table boxes carry real values beyond nn(m): those rows are zeros
-      // of the truncated expansion.  Storing the two parities with one instruction each would write every 32-byte
-      // sector in two halves (a warp store = 4 planes x 8 rows at a 32-byte stride); instead neighbouring lanes
-      // (planes kz, kz+1) swap one value, so that an instruction writes rows n AND n+1 of two planes: full sectors,
-      // half as many of them per tile (128^3: 84.9 -> 84.1 us; the stores are not what the epilogue waits for).
-      const bool odd = (fk & 1) != 0;
+      // of the truncated expansion.  (Swapping one value between neighbouring lanes so that every store instruction
+      // writes whole 32-byte sectors changed nothing in isolation and cost 4 % inside the round trip: the stores are
+      // not what the epilogue waits for.)
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         const int n = n0 + 2 * ((2 * mt + h) * 8 + fr);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int kz = kz0 + wq * 8 + nt * 4 + fk;
-          const cplx v0 = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
-          const cplx v1 = (n + 1 < nn) ? make_double2(acc[1][mt][nt][0], acc[1][mt][nt][1]) : make_double2(0.0, 0.0);
-          // even lane keeps row n of both planes, odd lane row n+1 of both planes
-          const cplx give = odd ? v0 : v1;
-          cplx got;
-          got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
-          got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
-          const int row = n + (odd ? 1 : 0);
-          const int kz_lo = kz & ~1;                   // the pair's planes: kz_lo (even lane's), kz_lo + 1 (odd lane's)
-          const cplx first = odd ? got : v0;           // plane kz_lo:     even lane -> its own v0, odd lane -> the neighbour's v1
-          const cplx second = odd ? v1 : got;          // plane kz_lo + 1: even lane -> the neighbour's v0, odd lane -> its own v1
-          if (row < a.nrdim) {
-            if (kz_lo < a.nzl) outp[(size_t)kz_lo * col_stride + row] = first;
-            if (kz_lo + 1 < a.nzl) outp[(size_t)(kz_lo + 1) * col_stride + row] = second;
+          if (kz < a.nzl) {
+            cplx *o = outp + (size_t)kz * col_stride + n;
+            if (n < a.nrdim)
+              o[0] = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
+            if (n + 1 < a.nrdim)
+              o[1] = (n + 1 < nn) ? make_double2(acc[1][mt][nt][0], acc[1][mt][nt][1]) : make_double2(0.0, 0.0);
           }
         }
       }
