@@ -541,6 +541,8 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
 
 // MIRROR: the launch also serves the mirrored planes (mirror_mode 1 or 2); compiled separately so that the plain
 // substitution keeps its code (the pass loop cost it 25 % at 256^3 when both lived in one kernel)
+// (80 registers, three CTAs per SM.  Forcing four -- 64 registers, 68 bytes of spills -- made the 256^3 ihelmp solve slower:
+// 1.46 vs 1.20 ms.)
 template <bool MIRROR>
 __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
