@@ -122,7 +122,10 @@ std::string trailer_bytes(const mlegs_field *s, const Layout &L) {
     t.append(s->space, 3);
   } else {
     char b[160];
-    // write(fo,*) s%ln, offsets ; write(fo,*) s%space   (list-directed)
+    // write(fo,*) s%ln, offsets ; write(fo,*) s%space   (list-directed).  The field widths of list-directed output are
+    // the compiler's choice (gfortran prints the real in a G25.17-style field and I12 integers), so this trailer is
+    // what the reference's list-directed READ accepts, not a byte copy of what a given compiler writes; the data
+    // records above follow the reference's explicit edit descriptors exactly.
     snprintf(b, sizeof(b), " %24.16E %11d %11d %11d\n %.3s\n", s->ln, s->nrchop_offset, s->npchop_offset,
              s->nzchop_offset, s->space);
     t = b;

@@ -1,8 +1,10 @@
 """msave / mload file formats (submodules/mlegs_scalar_io.f90:6-250) through the host halves of the C ABI: no GPU.
 
 The binary stream layout is checked byte for byte against an independent numpy writer of the reference's write
-statements; the formatted layout against the reference's edit descriptors ((3(1X,I10)), 1PE24.15E3); and the
-cooperative multi-rank write must produce exactly the file a single rank writes."""
+statements; the formatted layout against the reference's edit descriptors ((3(1X,I10)), 1PE24.15E3) -- the
+list-directed trailer (write(fo,*) s%ln, ...) has compiler-chosen field widths, so there the claim is only that the
+reference's list-directed read accepts it; and the cooperative multi-rank write must produce exactly the file a single
+rank writes."""
 import os
 import re
 import socket
