@@ -173,6 +173,7 @@ struct FftRegArgs {
   int nrdim;
   RowScale rs;           // fused r*u (r2c loads) / u/r (c2r stores) of the scalars in rs.mask
   PeerTable pt;
+  int dbg_copy;          // diagnostic (MLEGS_FFT_COPY=1): move the data with the kernel's access pattern, no transform
 };
 
 // x / b with the reciprocal y = RN(1/b) computed once per line: q = RN(x y), r = x - b q (exact in an fma),
@@ -272,6 +273,12 @@ __device__ __forceinline__ void fft_reg_tile(const FftRegArgs &a, long long blk)
       if (EXT && MODE == FFT_R2C_FWD && scaled) x = make_double2(x.x * rv, x.y * rv);
       v[j] = (MODE == FFT_C2C_BWD) ? cconj(x) : x;
     }
+  }
+  if (a.dbg_copy) {
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+      if (ok) gout[(long long)(t + T * j) * a.stride_pt] = v[j];
+    return;
   }
 
   // ---- pass 0 ----
@@ -460,6 +467,8 @@ int launch_fft_reg(FftMode mode, int n, const cplx *in, cplx *out, long long nli
     a.in[0] = in;
     a.out[0] = out;
   }
+  static const char *dbg = getenv("MLEGS_FFT_COPY");
+  a.dbg_copy = dbg && dbg[0] == '1';
   a.use_peer = peer != nullptr;
   a.nrdim = nrdim;
   if (peer) a.pt = *peer;

@@ -39,10 +39,10 @@ namespace mlegs {
 
 // NTC z planes per tile -> NTC/8 column groups of DMMA warps x 2 row groups, one producer warp per 8 planes (a bulk
 // copy is a warp-uniform instruction, UBLKCP, so the copies of one warp issue one after the other)
-template <int NTC>
+template <int NTC, int HW = 2>
 struct WsCfg {
   static constexpr int NCG = NTC / 8;          // column groups (8 z planes = 16 real columns each)
-  static constexpr int NCW = 2 * NCG;          // DMMA warps
+  static constexpr int NCW = HW * NCG;         // DMMA warps: HW row groups x NCG column groups
   static constexpr int NPW = NCG;              // producer warps
   static constexpr int CONS = 32 * NCW, PROD = 32 * NPW, THREADS = CONS + PROD;
 };
@@ -375,14 +375,14 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB) leg_backward_ws_ker
 // fold left in the DMMA warps' fragment path is one DADD per B fragment: (top + mirror) feeds the rows of one
 // parity, (top - mirror) the other.
 #define WSF_MT 128
-#define WSF_KC 32                        // radial points per stage
-#define WSF_LDK (WSF_KC + 4)             // complex elements per field row in shared memory (fragment reads conflict-free)
+// KC = radial points per stage (16 or 32); a field row in shared memory is KC + 4 complex elements long (fragment reads
+// conflict-free for KC = 16 and 32: the row stride is 8 mod 16 doubles)
 
-template <int NTC>
+template <int NTC, int KC>
 struct FwdStageWS {
-  double A[2][WSF_MT][16];               // two swizzled TMA boxes: [k / 16][n][k % 16, 16-byte chunks XOR (n & 7)]
-  double T[NTC][2 * WSF_LDK];            // f(i0 + k, kz), (re, im) interleaved
-  double Bm[NTC][2 * WSF_LDK];           // f(nr-1-i0-k, kz) at complex index WSF_KC-1-k
+  double A[KC / 16][WSF_MT][16];         // swizzled TMA boxes: [k / 16][n][k % 16, 16-byte chunks XOR (n & 7)]
+  double T[NTC][2 * (KC + 4)];           // f(i0 + k, kz), (re, im) interleaved
+  double Bm[NTC][2 * (KC + 4)];          // f(nr-1-i0-k, kz) at complex index KC-1-k
 };
 struct FwdCtxWS {
   const cplx *in;                        // f(0, m, kz0)
@@ -390,15 +390,17 @@ struct FwdCtxWS {
   double lnval;
   int nn, n0, kz0, mglob, valid;
 };
-template <int NTC, int NS>
+template <int NTC, int KC, int NS>
 struct FwdSmemWS {
-  FwdStageWS<NTC> st[NS];
+  FwdStageWS<NTC, KC> st[NS];
   FwdCtxWS ring[WS_RING];
   unsigned long long full[NS], empty[NS];
 };
-static_assert(sizeof(FwdSmemWS<32, 3>) <= 227 * 1024, "shared memory of the forward kernel");
-static_assert(2 * (sizeof(FwdSmemWS<16, 2>) + 1024) <= 227 * 1024, "two forward CTAs per SM");
-static_assert(sizeof(FwdStageWS<32>) % 1024 == 0 && sizeof(FwdStageWS<16>) % 1024 == 0,
+static_assert(sizeof(FwdSmemWS<32, 32, 3>) <= 227 * 1024, "shared memory of the forward kernel");
+static_assert(sizeof(FwdSmemWS<32, 16, 6>) <= 227 * 1024, "shared memory of the forward kernel (16-point stages)");
+static_assert(2 * (sizeof(FwdSmemWS<16, 32, 2>) + 1024) <= 227 * 1024, "two forward CTAs per SM");
+static_assert(sizeof(FwdStageWS<32, 32>) % 1024 == 0 && sizeof(FwdStageWS<16, 32>) % 1024 == 0 &&
+                  sizeof(FwdStageWS<32, 16>) % 1024 == 0,
               "swizzled boxes need 1024-byte alignment");
 
 // Tile order: row tile fastest, then z tile, then scalar, then column m (heaviest columns first).  The row tiles of one
@@ -452,17 +454,19 @@ __device__ __forceinline__ void tma_box3(void *dst, const CUtensorMap *tm, int c
       : "memory");
 }
 
-template <int NTC, int NS, int MINB>
-__global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
+// HW = row groups of DMMA warps (2: 64 rows per warp, 4: 32 rows per warp and four DMMA warps per SM sub-partition)
+template <int NTC, int KC, int NS, int MINB, int HW, int CREGS>
+__global__ void __launch_bounds__(WsCfg<NTC, HW>::THREADS, MINB)
     leg_forward_ws_kernel(LegArgs a, LegItemsF L, const __grid_constant__ CUtensorMap tmap) {
-  using Cfg = WsCfg<NTC>;
+  using Cfg = WsCfg<NTC, HW>;
+  constexpr int MT = 8 / HW;            // 8-row DMMA tiles of each parity per warp
   constexpr int CONS = Cfg::CONS, PROD = Cfg::PROD, NCG = Cfg::NCG;
   extern __shared__ __align__(1024) unsigned char smraw_f[];
-  FwdSmemWS<NTC, NS> &S = *reinterpret_cast<FwdSmemWS<NTC, NS> *>(smraw_f);   // no static shared memory: 1024-aligned
+  FwdSmemWS<NTC, KC, NS> &S = *reinterpret_cast<FwdSmemWS<NTC, KC, NS> *>(smraw_f);   // 1024-aligned
   if ((smem_u32(smraw_f) & 1023u) != 0) __trap();                              // the swizzled boxes rely on it
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t col_stride = (size_t)a.nrl * a.npl;
-  const int NCH = (a.nrh + WSF_KC - 1) / WSF_KC;
+  const int NCH = (a.nrh + KC - 1) / KC;
 
   if (tid == 0) {
 #pragma unroll
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
     // =============================== producer warps ===============================
     // warp pw: field rows (z planes) 8 pw .. 8 pw + 7: lanes 0-7 the top rows, lanes 8-15 the mirror rows; the first
     // producer thread also issues the two table boxes
+    if (CREGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
     const int pw = warp - Cfg::NCW;
     const int row_l = pw * 8 + (lane & 7);
     const bool is_top = lane < 8, is_mir = lane >= 8 && lane < 16;
@@ -504,36 +509,37 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
       for (int c = 0; c < NCH; ++c, ++g) {
         const int s = g % NS;
         if (g >= NS) mbar_wait(&S.empty[s], ((g / NS) + 1) & 1);
-        FwdStageWS<NTC> &B = S.st[s];
-        const int i0 = c * WSF_KC;
-        const int cnt = min(WSF_KC, a.nrh - i0);     // radial points of this stage (table columns beyond are TMA zero-fill)
+        FwdStageWS<NTC, KC> &B = S.st[s];
+        const int i0 = c * KC;
+        const int cnt = min(KC, a.nrh - i0);         // radial points of this stage (table columns beyond are TMA zero-fill)
         unsigned bytes = row_ok ? (unsigned)cnt * 16u : 0u;
-        if (tid == CONS) bytes += 2u * WSF_MT * 16u * 8u;
+        if (tid == CONS) bytes += (unsigned)(KC / 16) * WSF_MT * 16u * 8u;
         mbar_arrive_expect_tx(&S.full[s], bytes);
         if (tid == CONS) {
-          tma_box3(&B.A[0][0][0], &tmap, i0, x.n0, x.mglob, &S.full[s]);
-          tma_box3(&B.A[1][0][0], &tmap, i0 + 16, x.n0, x.mglob, &S.full[s]);
+#pragma unroll
+          for (int bx = 0; bx < KC / 16; ++bx) tma_box3(&B.A[bx][0][0], &tmap, i0 + 16 * bx, x.n0, x.mglob, &S.full[s]);
         }
-        if (row_ok && cnt < WSF_KC) {
+        if (row_ok && cnt < KC) {
           // radial points beyond nr/2 meet zero-filled table columns: keep stale NaN patterns out of the products
           double *row = is_top ? &B.T[row_l][2 * cnt] : &B.Bm[row_l][0];
-          for (int q = 0; q < 2 * (WSF_KC - cnt); ++q) row[q] = 0.0;
+          for (int q = 0; q < 2 * (KC - cnt); ++q) row[q] = 0.0;
         }
         if (row_ok) {
           if (is_top)
             bulk_g2s(&B.T[row_l][0], src_col + i0, (unsigned)cnt * 16u, &S.full[s]);
           else
-            bulk_g2s(&B.Bm[row_l][2 * (WSF_KC - cnt)], src_col + (a.nr - i0 - cnt), (unsigned)cnt * 16u, &S.full[s]);
+            bulk_g2s(&B.Bm[row_l][2 * (KC - cnt)], src_col + (a.nr - i0 - cnt), (unsigned)cnt * 16u, &S.full[s]);
         }
       }
     }
   } else {
     // =============================== consumer warps ===============================
     // warp (h, wq): row tiles t = 2 mt + h (8 rows of each parity = 16 consecutive n), real columns 16 wq .. 16 wq + 15
+    if (CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CREGS));
     const int h = warp / NCG, wq = warp % NCG;
     const int fr = lane >> 2, fk = lane & 3;
     const int swap = a.swap_parity;   // 0: even rows contract with the sum fold (eomul), 1: with the difference (oemul)
-    double acc[2][4][2][2];
+    double acc[2][MT][2][2];
 
     // Columns without a retained row have no tile: they are zeros (se = 0, ops:1898-1899).  Written here, by the DMMA
     // warps, while the first stages are in flight.  (Rows beyond the last row tile of a column WITH retained rows
@@ -552,21 +558,21 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
 
     // NACT: active row tiles of this warp; SWAP: 0 = even rows contract with the sum fold (eomul), 1 = with the
     // difference (oemul); LN: remove the log term from the real part of the m = 0 column (ops:193-195)
-    auto compute = [&](auto nact_c, auto swap_c, auto ln_c, const FwdStageWS<NTC> &B, int i0, double lnval) {
+    auto compute = [&](auto nact_c, auto swap_c, auto ln_c, const FwdStageWS<NTC, KC> &B, int i0, double lnval) {
       constexpr int NACT = decltype(nact_c)::value;
       constexpr int SWAP = decltype(swap_c)::value;
       constexpr bool LN = decltype(ln_c)::value != 0;
 #pragma unroll
-      for (int ks = 0; ks < WSF_KC / 4; ++ks) {
+      for (int ks = 0; ks < KC / 4; ++ks) {
         const int k = ks * 4 + fk;                  // radial point within the stage
         const int kk = k & 15, box = k >> 4;
-        double af[2][4], bf[2][2];
+        double af[2][MT], bf[2][2];
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < MT; ++mt)
             if (mt < NACT) {
-              const int nl = 16 * (2 * mt + h) + 2 * fr + p;
+              const int nl = 16 * (HW * mt + h) + 2 * fr + p;
               af[p][mt] = B.A[box][nl][(((kk >> 1) ^ (nl & 7)) << 1) + (kk & 1)];
             }
         double l1 = 0.0, l2 = 0.0;
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
         for (int nt = 0; nt < 2; ++nt) {
           const int col = wq * 16 + nt * 8 + fr;    // real column: plane col / 2, real or imaginary part
           double t = B.T[col >> 1][2 * k + (col & 1)];
-          double mr = B.Bm[col >> 1][2 * (WSF_KC - 1 - k) + (col & 1)];
+          double mr = B.Bm[col >> 1][2 * (KC - 1 - k) + (col & 1)];
           if (LN) {
             t -= l1;
             mr -= l2;
@@ -592,21 +598,18 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < MT; ++mt)
             if (mt < NACT) {
 #pragma unroll
               for (int nt = 0; nt < 2; ++nt) dmma884(acc[p][mt][nt][0], acc[p][mt][nt][1], af[p][mt], bf[p][nt]);
             }
       }
     };
-    auto compute_n = [&](auto swap_c, auto ln_c, int nact, const FwdStageWS<NTC> &B, int i0, double lnval) {
-      switch (nact) {
-        case 4: compute(IntK<4>{}, swap_c, ln_c, B, i0, lnval); break;
-        case 3: compute(IntK<3>{}, swap_c, ln_c, B, i0, lnval); break;
-        case 2: compute(IntK<2>{}, swap_c, ln_c, B, i0, lnval); break;
-        case 1: compute(IntK<1>{}, swap_c, ln_c, B, i0, lnval); break;
-        default: break;
-      }
+    auto compute_n = [&](auto swap_c, auto ln_c, int nact, const FwdStageWS<NTC, KC> &B, int i0, double lnval) {
+      if (MT == 4 && nact == 4) compute(IntK<(MT == 4 ? 4 : 1)>{}, swap_c, ln_c, B, i0, lnval);
+      else if (MT == 4 && nact == 3) compute(IntK<(MT == 4 ? 3 : 1)>{}, swap_c, ln_c, B, i0, lnval);
+      else if (nact == 2) compute(IntK<2>{}, swap_c, ln_c, B, i0, lnval);
+      else if (nact == 1) compute(IntK<1>{}, swap_c, ln_c, B, i0, lnval);
     };
 
     int g = 0;
@@ -616,22 +619,22 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
       const int nn = x.nn, n0 = x.n0, kz0 = x.kz0;
       cplx *outp = x.out;
       const double lnval = x.lnval;
-      const int nact = min(4, max(0, (nn - n0 - 16 * h + 31) >> 5));
+      const int nact = min(MT, max(0, (nn - n0 - 16 * h + 16 * HW - 1) / (16 * HW)));
 #pragma unroll
       for (int p = 0; p < 2; ++p)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) acc[p][i][j][0] = acc[p][i][j][1] = 0.0;
       for (int c = 0; c < NCH; ++c, ++g) {
         const int s = g % NS;
         mbar_wait(&S.full[s], (g / NS) & 1);
         if (__double_as_longlong(lnval) != 0) {
-          if (swap) compute_n(IntK<1>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
-          else compute_n(IntK<0>{}, IntK<1>{}, nact, S.st[s], c * WSF_KC, lnval);
+          if (swap) compute_n(IntK<1>{}, IntK<1>{}, nact, S.st[s], c * KC, lnval);
+          else compute_n(IntK<0>{}, IntK<1>{}, nact, S.st[s], c * KC, lnval);
         } else {
-          if (swap) compute_n(IntK<1>{}, IntK<0>{}, nact, S.st[s], c * WSF_KC, lnval);
-          else compute_n(IntK<0>{}, IntK<0>{}, nact, S.st[s], c * WSF_KC, lnval);
+          if (swap) compute_n(IntK<1>{}, IntK<0>{}, nact, S.st[s], c * KC, lnval);
+          else compute_n(IntK<0>{}, IntK<0>{}, nact, S.st[s], c * KC, lnval);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.empty[s]);
@@ -641,18 +644,20 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
       // of the truncated expansion.  (Swapping one value between neighbouring lanes so that every store instruction
       // writes whole 32-byte sectors changed nothing in isolation and cost 4 % inside the round trip: the stores are
       // not what the epilogue waits for.)
+      {
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        const int n = n0 + 2 * ((2 * mt + h) * 8 + fr);
+        for (int mt = 0; mt < MT; ++mt) {
+          const int n = n0 + 2 * ((HW * mt + h) * 8 + fr);
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const int kz = kz0 + wq * 8 + nt * 4 + fk;
-          if (kz < a.nzl) {
-            cplx *o = outp + (size_t)kz * col_stride + n;
-            if (n < a.nrdim)
-              o[0] = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
-            if (n + 1 < a.nrdim)
-              o[1] = (n + 1 < nn) ? make_double2(acc[1][mt][nt][0], acc[1][mt][nt][1]) : make_double2(0.0, 0.0);
+          for (int nt = 0; nt < 2; ++nt) {
+            const int kz = kz0 + wq * 8 + nt * 4 + fk;
+            if (kz < a.nzl) {
+              cplx *o = outp + (size_t)kz * col_stride + n;
+              if (n < a.nrdim)
+                o[0] = (n < nn) ? make_double2(acc[0][mt][nt][0], acc[0][mt][nt][1]) : make_double2(0.0, 0.0);
+              if (n + 1 < a.nrdim)
+                o[1] = (n + 1 < nn) ? make_double2(acc[1][mt][nt][0], acc[1][mt][nt][1]) : make_double2(0.0, 0.0);
+            }
           }
         }
       }
@@ -661,7 +666,7 @@ __global__ void __launch_bounds__(WsCfg<NTC>::THREADS, MINB)
         const int kz = kz0 + wq * 8 + (lane >> 2);
         if (kz < a.nzl) {
           cplx *o = outp + (size_t)kz * col_stride;
-          for (int n = n0 + WSF_MT + 4 * h + (lane & 3); n < a.nrdim; n += 8) o[n] = make_double2(0.0, 0.0);
+          for (int n = n0 + WSF_MT + 4 * h + (lane & 3); n < a.nrdim; n += 4 * HW) o[n] = make_double2(0.0, 0.0);
         }
       }
     }
@@ -682,8 +687,24 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 // big shape: 32 planes per tile, one CTA per SM; small shape: 16 planes per tile, two CTAs per SM
 #define WSB_BIG 32, 6, 1
 #define WSB_SMALL 16, 4, 2
-#define WSF_BIG 32, 3, 1
-#define WSF_SMALL 16, 2, 2
+// forward variants <NTC, KC, NS, MINB, HW, CREGS>; CREGS > 0: the DMMA warpgroups raise their register allowance to
+// CREGS (setmaxnreg) once the producer warpgroup has dropped to 40.  The registers come out of the CTA's own allocation
+// (threads x registers at launch): 640 x 96 here, so 104 is the most sixteen DMMA warps can get (112 never gets its
+// registers and the CTA hangs).
+#define WSF_BIG 32, 32, 3, 1, 2, 0        // 8 DMMA warps, 64 rows x 8 planes each
+#define WSF_SMALL 16, 32, 2, 2, 2, 0      // two CTAs per SM
+#define WSF_W16 32, 32, 3, 1, 4, 104      // 16 DMMA warps, 32 rows x 8 planes each: four per SM sub-partition
+
+template <int NTC, int KC, int NS, int MINB, int HW, int CREGS>
+static int fwd_set_smem() {
+  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel<NTC, KC, NS, MINB, HW, CREGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(FwdSmemWS<NTC, KC, NS>)));
+  return MLEGS_OK;
+}
+template <int NTC, int KC, int NS, int MINB, int HW, int CREGS>
+static void fwd_launch(int grid, const LegArgs &b, const LegItemsF &L, const CUtensorMap &tm, cudaStream_t st) {
+  leg_forward_ws_kernel<NTC, KC, NS, MINB, HW, CREGS><<<grid, WsCfg<NTC, HW>::THREADS, sizeof(FwdSmemWS<NTC, KC, NS>), st>>>(b, L, tm);
+}
 
 static int ws_setup() {
   if (g_ws_sms) return MLEGS_OK;
@@ -698,10 +719,9 @@ static int ws_setup() {
   CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<0, WSB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_b));
   CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<1, WSB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_b));
   CUDA_TRY(cudaFuncSetAttribute(leg_backward_ws_kernel<2, WSB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, small_b));
-  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel<WSF_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(FwdSmemWS<32, 3>)));
-  CUDA_TRY(cudaFuncSetAttribute(leg_forward_ws_kernel<WSF_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(FwdSmemWS<16, 2>)));
+  MLEGS_TRY(fwd_set_smem<WSF_BIG>());
+  MLEGS_TRY(fwd_set_smem<WSF_SMALL>());
+  MLEGS_TRY(fwd_set_smem<WSF_W16>());
   return MLEGS_OK;
 }
 
@@ -854,6 +874,12 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   MLEGS_TRY(table_tmap(tab, a.nrh, a.ne, c.p.npchop, &tm));
   const bool small = ws_small_shape(a, true);
   const int ntc = small ? 16 : 32;
+  // Sixteen DMMA warps for short contractions (tools/leg_bench.py, 8 scalars per launch: 128^3 80.0-81.9 us against
+  // 83.9-85.1 with eight; 256^3 963 / 979; 512^3 13.91 / 13.82 ms: the epilogue and tile turn-over that more warps
+  // shorten weigh less the longer a tile is); MLEGS_LEG_FWD=8|16 forces one for A/B timing
+  static const char *fv = getenv("MLEGS_LEG_FWD");
+  const bool w16 = !small && (fv ? atoi(fv) == 16 : a.nrh <= 128);
+  const int kc = 32;
   // tiles: (column with nn(m) > 0) x scalar x z tile x row tile of the widest column; nn(m) is non-increasing in m,
   // so the columns with work form a prefix
   LegItemsF L;
@@ -871,7 +897,7 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   L.total = total;
   L.mcount = mcount;
   L.ctr = nullptr;
-  if (!small && (a.nrh + WSF_KC - 1) / WSF_KC >= 8) {
+  if (!small && (a.nrh + kc - 1) / kc >= 8) {
     L.ctr = g_ws_ctr;
     CUDA_TRY(cudaMemsetAsync(g_ws_ctr, 0, sizeof(unsigned int), st));
   }
@@ -883,9 +909,11 @@ int launch_leg_forward_ws(const LegArgs &a, cudaStream_t st) {
   leg_alg_work(a, &wb, &wf);
   prof_begin("legendre_forward", st, wb, wf);
   if (small)
-    leg_forward_ws_kernel<WSF_SMALL><<<grid, WsCfg<16>::THREADS, sizeof(FwdSmemWS<16, 2>), st>>>(b, L, *tm);
+    fwd_launch<WSF_SMALL>(grid, b, L, *tm, st);
+  else if (w16)
+    fwd_launch<WSF_W16>(grid, b, L, *tm, st);
   else
-    leg_forward_ws_kernel<WSF_BIG><<<grid, WsCfg<32>::THREADS, sizeof(FwdSmemWS<32, 3>), st>>>(b, L, *tm);
+    fwd_launch<WSF_BIG>(grid, b, L, *tm, st);
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
