@@ -499,8 +499,10 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) band_solve_kernel(SolveArgs 
       // keep the factors: every later solve with this operator only runs the two substitutions
       __syncwarp();
       const long long c0 = a.fac_off[j] + (long long)(k - a.k0) * nn;   // first column of this system
-      double *fa = a.fac_ab + c0 * ldab;
-      for (int idx = lane; idx < ldab * nn; idx += 32) fa[idx] = AB[idx];
+      const int lu = kl + ku + 1;
+      double *fu = a.fac_ab + c0 * lu, *fl = a.fac_ab + a.fac_ncols * lu + c0 * kl;
+      for (int idx = lane; idx < lu * nn; idx += 32) fu[idx] = AB[(size_t)(idx / lu) * ldab + idx % lu];
+      for (int idx = lane; idx < kl * nn; idx += 32) fl[idx] = AB[(size_t)(idx / kl) * ldab + lu + idx % kl];
       for (int idx = lane; idx < nn; idx += 32) a.fac_piv[c0 + idx] = (unsigned char)piv[idx];
     }
     // ---- ztbsv: upper, no transpose, non-unit, bandwidth kv ----
@@ -566,7 +568,8 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
     if (MIRROR && pass == 1 && (kf == 0 || k < a.mirror_lo || k >= a.mirror_nz)) break;
     cplx *col = a.e + ((size_t)k * a.npl + j) * a.nrl;
     const bool special = (pass == 0 && a.special00 && mglob == 0 && k == 0);
-    const double *__restrict__ AB = a.fac_ab + c0 * ldab;
+    const double *__restrict__ FU = a.fac_ab + c0 * (kv + 1);
+    const double *__restrict__ FL = a.fac_ab + a.fac_ncols * (kv + 1) + c0 * kl;
     const unsigned char *__restrict__ piv = a.fac_piv + c0;
     for (int i = lane; i < nn; i += 32) {
       cplx v;
@@ -588,7 +591,7 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int cc = jb + 4 * h + (lane >> 3);
-          l[h] = (cc < nn && (lane & 7) < kl) ? __ldg(&AB[(size_t)cc * ldab + kv + 1 + (lane & 7)]) : 0.0;
+          l[h] = (cc < nn && (lane & 7) < kl) ? __ldg(&FL[(size_t)cc * kl + (lane & 7)]) : 0.0;
         }
         pv = (lane < 8 && jb + lane < nn) ? (int)__ldg(&piv[jb + lane]) : 0;
       };
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(CSOLVE_WARPS * 32) band_solve_cached_kernel(So
 #pragma unroll
         for (int sidx = 0; sidx < 8; ++sidx) {
           const int cc = jtop - sidx;
-          u[sidx] = (cc >= 0 && lane <= kv && lane <= cc) ? __ldg(&AB[(size_t)cc * ldab + kv - lane]) : 0.0;
+          u[sidx] = (cc >= 0 && lane <= kv && lane <= cc) ? __ldg(&FU[(size_t)cc * (kv + 1) + kv - lane]) : 0.0;
         }
       };
       loadU(nn - 1, ucur);
@@ -706,7 +709,8 @@ __global__ void __launch_bounds__(NSOLVE_WARPS * 32) band_solve_cached_narrow_ke
 #pragma unroll
     for (int off = NSOLVE_GROUP; off < 32; off <<= 1) nnw = max(nnw, __shfl_xor_sync(0xffffffffu, nnw, off));
     const long long c0 = have ? a.fac_off[j] + (long long)(kf - a.k0) * nn : 0;
-    const double *__restrict__ AB = a.fac_ab + c0 * ldab;
+    const double *__restrict__ FU = a.fac_ab + c0 * (kv + 1);
+    const double *__restrict__ FL = a.fac_ab + a.fac_ncols * (kv + 1) + c0 * kl;
     const unsigned char *__restrict__ piv = a.fac_piv + c0;
     for (int pass = 0; pass < (MIRROR ? 2 : 1); ++pass) {
       if (MIRROR && pass == 0 && a.mirror_mode == 2) continue;
@@ -734,7 +738,7 @@ __global__ void __launch_bounds__(NSOLVE_WARPS * 32) band_solve_cached_narrow_ke
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int cc = jb + u;
-            l[u] = (cc < nnp && gl >= 1 && gl <= kl) ? __ldg(&AB[(size_t)cc * ldab + kv + gl]) : 0.0;
+            l[u] = (cc < nnp && gl >= 1 && gl <= kl) ? __ldg(&FL[(size_t)cc * kl + gl - 1]) : 0.0;
             pv[u] = (cc < nnp && gl == 0) ? (int)__ldg(&piv[cc]) : 0;
           }
         };
@@ -786,9 +790,9 @@ __global__ void __launch_bounds__(NSOLVE_WARPS * 32) band_solve_cached_narrow_ke
 #pragma unroll
           for (int sidx = 0; sidx < 8; ++sidx) {
             const int cc = jtop - sidx;
-            u[sidx] = (cc >= 0 && cc < nnp && gl <= kv && gl <= cc) ? __ldg(&AB[(size_t)cc * ldab + kv - gl]) : 0.0;
+            u[sidx] = (cc >= 0 && cc < nnp && gl <= kv && gl <= cc) ? __ldg(&FU[(size_t)cc * (kv + 1) + kv - gl]) : 0.0;
             if (NSOLVE_GROUP == 16)
-              v[sidx] = (second && cc >= 0 && cc < nnp && g2 <= cc) ? __ldg(&AB[(size_t)cc * ldab + kv - g2]) : 0.0;
+              v[sidx] = (second && cc >= 0 && cc < nnp && g2 <= cc) ? __ldg(&FU[(size_t)cc * (kv + 1) + kv - g2]) : 0.0;
           }
         };
         loadU(nnw - 1, ucur, vcur);
@@ -851,6 +855,7 @@ struct FactorEntry {
   double *ab = nullptr;
   unsigned char *piv = nullptr;
   long long *off = nullptr;
+  long long ncols = 0;
   size_t bytes = 0;
   unsigned long long stamp = 0;
 };
@@ -945,6 +950,7 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
   a.fac_ab = nullptr;
   a.fac_piv = nullptr;
   a.fac_off = nullptr;
+  a.fac_ncols = 0;
 
   // ---- cached factors? ----
   FactorEntry *hit = nullptr;
@@ -958,6 +964,7 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
     a.fac_ab = hit->ab;
     a.fac_piv = hit->piv;
     a.fac_off = hit->off;
+    a.fac_ncols = hit->ncols;
     const int nsys = a.npl * a.nk;
     size_t smem = (size_t)CSOLVE_WARPS * 2 * a.nnmax * sizeof(double);
     static size_t attr_set = 0;
@@ -1045,10 +1052,12 @@ int launch_band_solve(SolveArgs a, cudaStream_t st) {
       if (ok) {
         CUDA_TRY(cudaMemcpyAsync(e.off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));   // `off` goes out of scope
+        e.ncols = (long long)ncols;
         g_fcache.push_back(e);
         a.fac_ab = e.ab;
         a.fac_piv = e.piv;
         a.fac_off = e.off;
+        a.fac_ncols = e.ncols;
       } else {
         cudaGetLastError();
         free_entry(e);

@@ -227,7 +227,11 @@ struct SolveArgs {
   double *ws_global;
   int *flag;
   // factor cache (filled on the first solve with a given operator, reused by every later right-hand side)
-  double *fac_ab;                // LAPACK band storage of the LU factors, all systems
+  double *fac_ab;                // LU factors of all systems: the U rows (kl + ku + 1 per matrix column) of every column
+                                 // first, then the L multipliers (kl per column) -- each substitution sweep streams
+                                 // only its own part, contiguously (LAPACK's interleaved band storage made both sweeps
+                                 // fetch 1.5x the factor bytes from HBM: 32-byte sectors of 200-byte columns)
+  long long fac_ncols;           // matrix columns in the set: the L part starts at fac_ab + fac_ncols (kl + ku + 1)
   unsigned char *fac_piv;        // pivot offsets jp (0..kl) per column
   const long long *fac_off;      // per local column j: offset (in columns) of system (j, k0); see launch_band_solve
   // The operator of plane k only contains ak(k)^2 = ak(nz-k)^2: the cached substitution can serve plane nz-k with the
