@@ -70,6 +70,103 @@ __global__ void __launch_bounds__(256) slab_ship_kernel(PeerTable t, ShipSrc src
   dist_finish_put(t, gridDim.x);
 }
 
+// The same runs moved by the TMA unit: one thread per CTA streams chunks of a run through a ring of shared-memory
+// stages -- cp.async.bulk global -> shared (mbarrier completion), cp.async.bulk shared -> the peer's window (bulk-group
+// completion) -- so the NVLink writes leave as whole bursts instead of one 16-byte store per thread, and the SM's LSU
+// and registers stay out of the data path.
+#define SHIP_STAGES 4
+#define SHIP_CHUNK 8192
+__global__ void __launch_bounds__(32) slab_ship_tma_kernel(PeerTable t, ShipSrc src, int nfld, int nz, int npdim) {
+  __shared__ __align__(128) unsigned char buf[SHIP_STAGES][SHIP_CHUNK];
+  __shared__ unsigned long long full[SHIP_STAGES];
+  const int me = t.rank, P = t.nranks, mc = t.m_cnt[me];
+  const long long nruns = (long long)nfld * P * nz;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SHIP_STAGES; ++s) {
+      unsigned a = (unsigned)__cvta_generic_to_shared(&full[s]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(a) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    // chunk c of this CTA: runs blockIdx.x, blockIdx.x + gridDim.x, ..., each cut into pieces of SHIP_CHUNK bytes
+    long long run_l = blockIdx.x, run_s = blockIdx.x;     // run of the next chunk to load / to store
+    unsigned off_l = 0, off_s = 0;                        // byte offset inside that run
+    auto locate = [&](long long run, const char **sp, char **dp, unsigned *bytes) {
+      const int k = (int)(run % nz);
+      const long long rest = run / nz;
+      const int q = (int)((me + 1 + rest % P) % P);
+      const int fld = (int)(rest / P);
+      const int len = mc * t.r_cnt[q];
+      *sp = reinterpret_cast<const char *>(src.p[fld] + (size_t)t.r_off[q] * mc * nz + (size_t)k * len);
+      *dp = reinterpret_cast<char *>(reinterpret_cast<cplx *>(reinterpret_cast<char *>(t.base[q]) + t.data_off +
+                                                               fld * t.fstride) +
+                                     ((size_t)k * npdim + t.m_off[me]) * t.r_cnt[q]);
+      *bytes = (unsigned)len * 16u;
+    };
+    auto load = [&](int i) {            // chunk i -> stage i % SHIP_STAGES; false when the CTA has no more chunks
+      while (run_l < nruns) {
+        const char *sp;
+        char *dp;
+        unsigned bytes;
+        locate(run_l, &sp, &dp, &bytes);
+        if (off_l >= bytes) {
+          run_l += gridDim.x;
+          off_l = 0;
+          continue;
+        }
+        const unsigned n = min(bytes - off_l, (unsigned)SHIP_CHUNK);
+        const int s = i % SHIP_STAGES;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&full[s]);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&buf[s][0]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                     "l"(sp + off_l), "r"(n), "r"(bar)
+                     : "memory");
+        off_l += n;
+        return true;
+      }
+      return false;
+    };
+    int loaded = 0;
+    for (; loaded < SHIP_STAGES - 1; ++loaded)
+      if (!load(loaded)) break;
+    bool more = loaded == SHIP_STAGES - 1;
+    for (int i = 0; i < loaded; ++i) {
+      // store chunk i
+      const char *sp;
+      char *dp;
+      unsigned bytes;
+      for (;;) {
+        locate(run_s, &sp, &dp, &bytes);
+        if (off_s < bytes) break;
+        run_s += gridDim.x;
+        off_s = 0;
+      }
+      const unsigned n = min(bytes - off_s, (unsigned)SHIP_CHUNK);
+      const int s = i % SHIP_STAGES;
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&full[s]);
+      const unsigned parity = (unsigned)((i / SHIP_STAGES) & 1);
+      asm volatile(
+          "{\n.reg .pred p;\nSHIP_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra SHIP_DONE;\nbra "
+          "SHIP_WAIT;\nSHIP_DONE:\n}\n" ::"r"(bar),
+          "r"(parity)
+          : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dp + off_s),
+                   "r"((unsigned)__cvta_generic_to_shared(&buf[s][0])), "r"(n)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      off_s += n;
+      // refill the stage whose store was committed one iteration ago (chunk i - 1's): at most this iteration's
+      // group may still be reading shared memory
+      if (more) {
+        asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+        if (load(loaded)) ++loaded; else more = false;
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+  }
+  dist_finish_put(t, gridDim.x);
+}
+
 int launch_slab_ship(const PeerTable &t, const FieldBatch &fb, cudaStream_t st) {
   Context &c = ctx();
   ShipSrc src;
@@ -81,9 +178,16 @@ int launch_slab_ship(const PeerTable &t, const FieldBatch &fb, cudaStream_t st) 
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const long long nruns = (long long)fb.n * c.nranks * c.nzdim;
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(nruns, (long long)sms * 8));
+  static const char *mode = getenv("MLEGS_SHIP");        // "simt" / "tma": A/B timing
+  const bool tma = mode ? mode[0] == 't' : false;
   prof_begin("exchange_12_ship", st);
-  slab_ship_kernel<<<grid, 256, 0, st>>>(t, src, fb.n, c.nzdim, c.npdim);
+  if (tma) {
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(nruns, (long long)sms * 4));
+    slab_ship_tma_kernel<<<grid, 32, 0, st>>>(t, src, fb.n, c.nzdim, c.npdim);
+  } else {
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(nruns, (long long)sms * 8));
+    slab_ship_kernel<<<grid, 256, 0, st>>>(t, src, fb.n, c.nzdim, c.npdim);
+  }
   prof_end(st);
   KERNEL_CHECK();
   return MLEGS_OK;
