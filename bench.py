@@ -562,9 +562,37 @@ def run_native(args):
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    # what PCIe gives this GPU with both directions busy (pinned 64 MB buffers, copy engines): the ceiling of the e2e rate
+    duplex = None
+    if world == 1:
+        nb_ = 64 << 20
+        hi, ho = torch.empty(nb_, dtype=torch.uint8).pin_memory(), torch.empty(nb_, dtype=torch.uint8).pin_memory()
+        di, do = torch.empty(nb_, dtype=torch.uint8, device="cuda"), torch.empty(nb_, dtype=torch.uint8, device="cuda")
+        sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(2 + 8):
+            if it == 2:
+                torch.cuda.synchronize()
+                ev0.record()
+                sa.wait_event(ev0)
+                sb.wait_event(ev0)
+            with torch.cuda.stream(sa):
+                di.copy_(hi, non_blocking=True)
+            with torch.cuda.stream(sb):
+                ho.copy_(do, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(sa)
+        torch.cuda.current_stream().wait_stream(sb)
+        ev1.record()
+        torch.cuda.synchronize()
+        duplex = nb_ / (ev0.elapsed_time(ev1) / 8 * 1e-3) / 1e9
+        del hi, ho, di, do
+    e2e_bytes = ne2e * 16 * (n_ppp + n_fff)
     e2e = {"value": ne2e * dof / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": ne2e * 16 * (n_ppp + n_fff), "d2h_bytes_per_step": ne2e * 16 * (n_ppp + n_fff),
+           "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
            "ms_per_step": e2e_ms, "fields_per_step": ne2e,
+           "pcie_GBps_per_direction": e2e_bytes / (e2e_ms * 1e-3) / 1e9,
+           "pcie_duplex_peak_GBps": duplex,
+           "pcie_frac": (e2e_bytes / (e2e_ms * 1e-3) / 1e9 / duplex) if duplex else None,
            "api": "mlegs_b200_trans_host_batch (host s%e in, host s%e out for every field of the batch; H2D, "
                   "transform and D2H pipelined), pinned host arrays; bytes are per rank"}
 
