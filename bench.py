@@ -648,8 +648,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--fields", type=int, default=0)
-    ap.add_argument("--batch", type=int, default=8,
-                    help="scalars per mlegs_b200_trans_many call (1: one mlegs_b200_trans per scalar)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="scalars per mlegs_b200_trans_many call (1: one mlegs_b200_trans per scalar; 0 = default: 32 on "
+                         "one GPU -- a launch costs ~9 us before its first byte moves, tools/rt_bench.py -- and 8 on "
+                         "several, what one exchange epoch carries)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-step", action="store_true", help="skip the q-vortex time-step section")
     ap.add_argument("--no-step512", action="store_true", help="N = 8: skip the 512^3 time step")
@@ -658,6 +660,8 @@ def main():
     ap.add_argument("--weak", default="nz", choices=["nz", "fields"],
                     help="N > 1: grow NZ with N (default, DOF per GPU fixed) or grow the batch of cubic fields")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = 32 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 8
     if args.shape:
         global SHAPE
         SHAPE = tuple(int(v) for v in args.shape.split(","))

@@ -357,9 +357,9 @@ int mlegs_b200_dist_window(void **dev_ptr, size_t *bytes, unsigned char handle64
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   static_assert(sizeof(WinHeader) <= DIST_FLAG_BYTES, "header size");
   if (!c.d_window) {
-    // W0/W1 carry up to MLEGS_MAXB scalars per epoch (batched transforms), within 8 GB per rank
+    // W0/W1 carry up to 8 scalars per epoch (batched transforms; one-GPU launches take up to MLEGS_MAXB = 32), within 8 GB per rank
     g_dist.fbytes = align256(c.field_bytes);
-    g_dist.wbatch = (int)std::max<size_t>(1, std::min<size_t>(MLEGS_MAXB, ((size_t)8 << 30) / (2 * g_dist.fbytes)));
+    g_dist.wbatch = (int)std::max<size_t>(1, std::min<size_t>(std::min(MLEGS_MAXB, 8), ((size_t)8 << 30) / (2 * g_dist.fbytes)));
     g_dist.wstride = g_dist.fbytes * g_dist.wbatch;
     size_t total = win_data_offset() + 2 * g_dist.wstride;
     CUDA_TRY(cudaMalloc(&c.d_window, total));

@@ -10,7 +10,7 @@ typedef double2 cplx;
 
 // Several independent scalars of identical layout handled by ONE launch (the three components of a vector field,
 // ops:1503-1505; a batch of scalars in mlegs_b200_trans_many): the field index is a grid dimension.
-#define MLEGS_MAXB 8
+#define MLEGS_MAXB 32
 struct FieldBatch {
   int n = 0;
   const cplx *in[MLEGS_MAXB];

@@ -84,7 +84,7 @@ struct Context {
   double *d_vtab = nullptr, *d_dtab = nullptr;
   // scratch
   void *d_scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // field-sized work buffers
-  void *d_batch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // trans_many, lazy
+  void *d_batch[32] = {};   // trans_many, lazy
   double *d_cossin_p = nullptr;  // cos / sin of the np azimuthal collocation angles (on-device initial conditions)
   static const int RED_DOUBLES = 32768;
   size_t field_bytes = 0;

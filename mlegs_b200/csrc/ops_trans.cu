@@ -285,7 +285,7 @@ size_t dist_field_stride();
 // of place, which replaces a field copy).
 struct TransOpts {
   unsigned rs_mask = 0;
-  const void *src[MLEGS_MAXB] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void *src[MLEGS_MAXB] = {};
 };
 
 static int trans_group(int n, mlegs_field *const *s, int cur, int dst, const TransOpts *opt = nullptr, int i0 = 0) {
@@ -302,9 +302,10 @@ static int trans_group(int n, mlegs_field *const *s, int cur, int dst, const Tra
   }
   const bool foreign_src = at[0] != home[0];
   RowScale rs;
-  if (opt && ((opt->rs_mask >> i0) & ((1u << n) - 1u))) {
+  const unsigned nmask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  if (opt && ((opt->rs_mask >> i0) & nmask)) {
     rs.r = c.d_r;
-    rs.mask = (opt->rs_mask >> i0) & ((1u << n) - 1u);
+    rs.mask = (opt->rs_mask >> i0) & nmask;
     rs.nr = c.p.nr;
   }
   bool rows_zero = false, in_transit = false;

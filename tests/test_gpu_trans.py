@@ -151,7 +151,7 @@ def test_roundtrip_128_config_and_host_entry():
 
 
 @pytest.mark.parametrize("case", ["gate2d", "gate3d", "radix35", "cube64"])
-@pytest.mark.parametrize("nf", [2, 3, 11])
+@pytest.mark.parametrize("nf", [2, 3, 11, 33])
 def test_trans_many_is_bit_identical_to_trans(case, nf):
     """mlegs_b200_trans_many: one launch per stage over all scalars; same arithmetic per scalar as trans()."""
     kit, ok = _setup(case)
