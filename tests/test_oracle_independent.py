@@ -52,3 +52,58 @@ def test_basis_functions_against_mpmath_legenp(kit3d):
     # the nodes themselves are double-precision numbers (sinit:187): evaluating the exact function AT the stored node
     # leaves rounding of the 50-digit recurrence's result only
     assert worst < 5e-13, worst
+
+
+def _radial_values(kit, s):
+    """Radial synthesis of every (m, k) column of an FFF coefficient array (the third axis is only carried along)."""
+    s.space = "FFP"
+    mo.rtrans_backward(s, kit)
+    return s.e
+
+
+@pytest.mark.parametrize("m", [0, 1, 3, 8])
+def test_band_operators_against_legendre_identities(kit3d, m):
+    """xxdx = r d/dr and del2 = (1/r) d/dr (r d/dr) - m^2/r^2 - ak(k)^2 of a single basis function: the oracle's band
+    tables (the coefficient formulas of sdiff:6-152, which the device kernels tabulate too) followed by its radial
+    synthesis, against derivatives built from mpmath's legenp with the textbook identities only --
+    (1 - x^2) P' = (n + 1) x P_n^m - (n - m + 1) P_{n+1}^m (DLMF 14.10.5), P'' from Legendre's equation, and the chain
+    rule through x = (r^2 - L^2) / (r^2 + L^2)."""
+    mpmath.mp.dps = 40
+    kit = kit3d
+    ell = mpmath.mpf(kit.p.ell)
+    nn = int(kit.chops[m])
+    nodes = [0, 3, 9, 17, 24, 31, 40, 47]
+    for j in (0, 1, 6, nn - 4):
+        n = m + j
+        norm = mpmath.sqrt(mpmath.mpf(2 * n + 1) / 2 * mpmath.factorial(n - m) / mpmath.factorial(n + m))
+        fv, d1v, d2v, rv = [], [], [], []
+        for i in nodes:
+            x = mpmath.mpf(float(kit.x[i]))
+            r = ell * mpmath.sqrt((1 + x) / (1 - x))
+            p0 = mpmath.legenp(n, m, x, type=2)
+            p1 = mpmath.legenp(n + 1, m, x, type=2)
+            dp = ((n + 1) * x * p0 - (n - m + 1) * p1) / (1 - x * x)
+            ddp = (2 * x * dp - (n * (n + 1) - mpmath.mpf(m * m) / (1 - x * x)) * p0) / (1 - x * x)
+            den = r * r + ell * ell
+            xr = 4 * r * ell * ell / den ** 2
+            xrr = 4 * ell * ell * (ell * ell - 3 * r * r) / den ** 3
+            rv.append(r)
+            fv.append(norm * p0)
+            d1v.append(norm * dp * xr)
+            d2v.append(norm * (ddp * xr * xr + dp * xrr))
+        for k in (0, 1):
+            ak = mpmath.mpf(float(kit.ak[k]))
+            for op in ("xxdx", "del2"):
+                s = mo.scalar_init(kit, "FFF")
+                s.e[j, m, k] = 1.0
+                getattr(mo, op)(s, kit)
+                got = _radial_values(kit, s)[:, m, k]
+                if op == "xxdx":
+                    exact = np.array([float(r * d1) for r, d1 in zip(rv, d1v)])
+                else:
+                    exact = np.array([float(d2 + d1 / r - (mpmath.mpf(m * m) / (r * r) + ak * ak) * f)
+                                      for r, f, d1, d2 in zip(rv, fv, d1v, d2v)])
+                scale = max(np.max(np.abs(exact)), 1e-30)
+                err = np.max(np.abs(got[nodes].real - exact)) / scale
+                assert err < 2e-11, (op, m, j, k, err)
+                assert np.max(np.abs(got[nodes].imag)) <= 1e-13 * scale
