@@ -120,7 +120,9 @@ int mlegs_b200_trans(mlegs_field *s, const char to[3]);                   /* ops
 /* trans() of n scalars that agree in space and chopping offsets -- the components of a vector field
  * (ops:1503-1505 transforms vr, vp, vz back to back) or the scalars of a multi-field app: every stage is ONE
  * launch over all of them (the scalar index is a grid dimension), results are bit-identical to n trans() calls.
- * Scalars in mixed states, or several ranks (the exchange window holds one scalar), fall back to a loop. */
+ * A launch carries up to 32 scalars (larger n goes in groups); on several ranks a group is what one exchange epoch
+ * carries (up to 8 slabs per window) and shares one fused exchange and one barrier per one-way transform.  Scalars in
+ * mixed states fall back to a loop of trans(). */
 int mlegs_b200_trans_many(int n, mlegs_field *const *s, const char to[3]);
 /* Reference-facing call on a HOST array (the Fortran s%e): H2D, trans, D2H. */
 int mlegs_b200_trans_host(void *host_e, const char from[3], const char to[3], double ln);
