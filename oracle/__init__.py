@@ -8,5 +8,8 @@ PARITY UNPINNED: the reference (Fortran 2008 + MPI + FFTE + FM + LAPACK)
 cannot be compiled in this image (no Fortran compiler, no MPI) and its own
 test-suite asserts no numeric value.  The oracle is therefore pinned only
 against the analytic known-answers listed in SURVEY.md section 4.3
-(tests/test_oracle_analytic.py); see DESIGN.md.
+(tests/test_oracle_analytic.py) and against third-party evaluations of its
+tables (tests/test_oracle_independent.py: numpy's Gauss-Legendre rule, mpmath's
+legenp for the basis functions and for the xxdx / del2 band tables; LAPACK's
+own zgbtrf/zgbtrs through scipy for the band solves); see DESIGN.md.
 """

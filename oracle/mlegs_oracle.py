@@ -1,8 +1,9 @@
 """NumPy restatement of the MLegS (v1.1.3) spectral-transform / nonlinear-term path.
 
 TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  PARITY UNPINNED (the
-reference cannot be compiled here; only the analytic known-answers of
-SURVEY.md section 4.3 pin this file, see tests/test_oracle_analytic.py).
+reference cannot be compiled here; the analytic known-answers of SURVEY.md
+section 4.3, tests/test_oracle_analytic.py, and third-party evaluations of the
+tables, tests/test_oracle_independent.py, are what pins this file).
 
 Single process, global arrays.  A field is a complex128 array of shape
 (nrdim, npdim, nzdim) in Fortran (column-major) order, i.e. exactly the memory
