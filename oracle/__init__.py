@@ -11,5 +11,7 @@ against the analytic known-answers listed in SURVEY.md section 4.3
 (tests/test_oracle_analytic.py) and against third-party evaluations of its
 tables (tests/test_oracle_independent.py: numpy's Gauss-Legendre rule, mpmath's
 legenp for the basis functions and for the xxdx / del2 band tables; LAPACK's
-own zgbtrf/zgbtrs through scipy for the band solves); see DESIGN.md.
+own zgbtrf/zgbtrs through scipy for the band solves; the full transform both
+ways against the triple sum the reference's docs/tutorial/initialization.md:154
+publishes, summed term by term); see DESIGN.md.
 """
