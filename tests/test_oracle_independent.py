@@ -1,7 +1,13 @@
-"""Third-party pins of the oracle's tables (the reference holds no numbers, see test_oracle_analytic.py): the quadrature
-against numpy's Gauss-Legendre rule and the orthonormal mapped associated Legendre functions against mpmath's
-`legenp` (type 2: Ferrers functions with the Condon-Shortley phase) over a spread of degrees, orders and nodes --
-not only the two closed forms of the tutorial."""
+"""Pins of the oracle that do not come from the oracle (the reference holds no numbers, see test_oracle_analytic.py).
+
+Third-party evaluations: the quadrature against numpy's Gauss-Legendre rule; the orthonormal mapped associated Legendre
+functions against mpmath's `legenp` (type 2: Ferrers functions with the Condon-Shortley phase) over a spread of degrees,
+orders and nodes; the xxdx / del2 band tables against derivatives built from `legenp` and textbook identities.
+
+The reference's own PUBLISHED definitions, evaluated term by term: the transform both ways against the triple sum of
+docs/tutorial/initialization.md:154; tp2vec against the curl formulas of docs/tutorial/vector_field.md:18,58-62 (and
+vec2tp as its inverse on a field with azimuthal and axial structure); ihelm / ihelmp as inverses of the operator applied
+as repeated del2; febe / abcn against the discretisation of docs/tutorial/time_integration.md:160-169, 381-390."""
 import math
 
 import mpmath
@@ -204,3 +210,193 @@ def test_analysis_equals_the_quadrature_of_the_definition(kit_small, basis_small
         nn = int(kit.chops[m])
         assert np.max(np.abs(got[:nn, m] - want[:nn, m])) / np.max(np.abs(want[:nn, m])) < 1e-13, m
         assert not np.any(got[nn:, m])                       # beyond the triangular truncation: exact zeros
+
+
+# ---- the toroidal-poloidal reconstruction from its published definition ---------------------------------------------
+# docs/tutorial/vector_field.md:18,58-62:  V = curl(psi e_z) + curl curl(chi e_z), i.e.
+#     V_r = (1/r) d psi/d phi + d^2 chi/(dr dz),  V_phi = - d psi/dr + (1/r) d^2 chi/(d phi dz),  V_z = - del_perp^2 chi.
+# One mode each for psi and chi, differentiated by hand (mpmath legenp + DLMF 14.10.5 + Legendre's equation + the chain
+# rule through the map), against the oracle's tp2vec (band tables, chop offsets, three backward transforms, the 1/r).
+
+def _mode_and_derivatives(kit, n, m, nodes):
+    """orthonormal P_{L_n}^m and its first two r-derivatives at the given node indices (mpmath numbers)."""
+    ell = mpmath.mpf(kit.p.ell)
+    norm = mpmath.sqrt(mpmath.mpf(2 * n + 1) / 2 * mpmath.factorial(n - m) / mpmath.factorial(n + m))
+    out = []
+    for i in nodes:
+        x = mpmath.mpf(float(kit.x[i]))
+        r = ell * mpmath.sqrt((1 + x) / (1 - x))
+        p0 = mpmath.legenp(n, m, x, type=2)
+        p1 = mpmath.legenp(n + 1, m, x, type=2)
+        dp = ((n + 1) * x * p0 - (n - m + 1) * p1) / (1 - x * x)
+        ddp = (2 * x * dp - (n * (n + 1) - mpmath.mpf(m * m) / (1 - x * x)) * p0) / (1 - x * x)
+        den = r * r + ell * ell
+        xr = 4 * r * ell * ell / den ** 2
+        xrr = 4 * ell * ell * (ell * ell - 3 * r * r) / den ** 3
+        out.append((r, norm * p0, norm * dp * xr, norm * (ddp * xr * xr + dp * xrr)))
+    return out
+
+
+@pytest.mark.parametrize("m,k,jpsi,jchi", [(3, 1, 2, 1), (1, 3, 0, 4), (5, 0, 3, 2)])
+def test_tp2vec_equals_the_published_curl_formulas(kit3d, m, k, jpsi, jchi):
+    mpmath.mp.dps = 40
+    kit = kit3d
+    nr, npts, nz = kit.p.nr, kit.p.np, kit.p.nz
+    nph = npts // 2
+    cpsi, cchi = 0.8 - 0.3j, -0.4 + 0.9j
+    psi, chi = mo.scalar_init(kit, "FFF"), mo.scalar_init(kit, "FFF")
+    psi.e[jpsi, m, k] = cpsi
+    chi.e[jchi, m, k] = cchi
+    vr, vp, vz = mo.tp2vec(psi, chi, kit)
+
+    nodes = list(range(0, nr, 3))
+    kap = float(kit.ak[k])                        # axial wavenumber 2 pi k' / zlen (k' signed)
+    P = _mode_and_derivatives(kit, m + jpsi, m, nodes)
+    C = _mode_and_derivatives(kit, m + jchi, m, nodes)
+    phi = 2 * np.pi * np.arange(npts) / npts
+    z = kit.p.zlen * np.arange(nz) / nz
+    E = np.exp(1j * (m * phi[:, None] + kap * z[None, :]))            # [p, l]
+    amp_r = np.array([complex(1j * m * cpsi * p0 / r + 1j * kap * cchi * c1) for (r, p0, _, _), (_, _, c1, _) in zip(P, C)])
+    amp_p = np.array([complex(-cpsi * p1 - m * kap * cchi * c0 / r) for (r, _, p1, _), (_, c0, _, _) in zip(P, C)])
+    amp_z = np.array([complex(-cchi * (c2 + c1 / r - mpmath.mpf(m * m) * c0 / (r * r))) for (r, c0, c1, c2) in C])
+    for got_s, amp, name in ((vr, amp_r, "vr"), (vp, amp_p, "vp"), (vz, amp_z, "vz")):
+        assert got_s.space == "PPP"
+        got = np.empty((nr, npts, nz))
+        got[:, 0::2, :] = got_s.e[:nr, :nph, :nz].real
+        got[:, 1::2, :] = got_s.e[:nr, :nph, :nz].imag
+        want = 2.0 * (amp[:, None, None] * E[None, :, :]).real          # the m < 0 partner is the conjugate
+        scale = np.max(np.abs(want))
+        assert scale > 0
+        assert np.max(np.abs(got[nodes] - want)) / scale < 5e-11, name
+
+
+def test_vec2tp_inverts_the_pinned_tp2vec_on_a_3d_field(kit3d):
+    """vec2tp (ops:1308-1453: psi = -del_perp^-2 (curl V)_z, chi = -del_perp^-2 V_z, docs/tutorial/vector_field.md:50-52)
+    must return the (psi, chi) that tp2vec -- pinned term by term above -- was given, for a field with azimuthal AND axial
+    structure (the tutorial's q-vortex only exercises m = 0, k = 0).  The gauge is the reference's: both scalars vanish
+    at infinity (zeroat1), which fixes the otherwise free P_{L_0}^0 component."""
+    kit = kit3d
+    rng = np.random.default_rng(5)
+
+    def smooth_random():
+        s = mo.scalar_init(kit, "FFF")
+        for m in range(9):
+            for k in (0, 1, 3):
+                if m == 0 and k == 0:
+                    continue
+                s.e[:10, m, k] = (rng.standard_normal(10) + 1j * rng.standard_normal(10)) * np.exp(-np.arange(10) / 3)
+        s.e[:, 0, 3] = np.conj(s.e[:, 0, 1])      # a real field: the m = 0 column is Hermitian in k
+        mo.chop(s, kit)
+        mo.zeroat1(s, kit)
+        return s
+
+    psi, chi = smooth_random(), smooth_random()
+    vr, vp, vz = mo.tp2vec(psi, chi, kit)
+    psi2, chi2 = mo.scalar_init(kit, "FFF"), mo.scalar_init(kit, "FFF")
+    mo.vec2tp(vr, vp, vz, psi2, chi2, kit)
+    assert np.linalg.norm(psi2.e - psi.e) / np.linalg.norm(psi.e) < 1e-12
+    assert np.linalg.norm(chi2.e - chi.e) / np.linalg.norm(chi.e) < 5e-12
+    assert abs(psi2.ln) < 1e-13 and abs(chi2.ln) < 1e-13
+
+
+@pytest.mark.parametrize("power,alpha,beta", [(4, 50.0, -3.0), (6, -200.0, 2.0), (8, 1.0e4, 0.5)])
+def test_ihelmp_inverts_helmp_built_from_the_pinned_del2(kit3d, power, alpha, beta):
+    """helmp = del^p + beta del^2 + alpha applied as repeated del2 (pinned against Legendre's equation above); ihelmp must
+    undo it: LAPACK's zgbtrf/zgbtrs on the band product the oracle assembles (ops:958-965) against the operator applied
+    term by term.  Signs as the integrators use them (definite operators).  The axial Nyquist plane is left empty: with
+    nzchop = nz/2 + 1 the reference's two k loops both visit it (kept, k_ranges), so there the two are not inverses."""
+    kit = kit3d
+    rng = np.random.default_rng(7)
+    s = mo.scalar_init(kit, "FFF")
+    s.e[:] = (rng.standard_normal(s.e.shape) + 1j * rng.standard_normal(s.e.shape)) \
+        * np.exp(-np.arange(s.e.shape[0]) / 4.0)[:, None, None]
+    s.e[:, :, kit.p.nz // 2] = 0.0
+    mo.chop(s, kit)
+    x = s.copy()
+    mo.ihelmp(x, power, alpha, beta, kit)
+    y = x.copy()
+    mo.helmp(y, power, alpha, beta, kit)
+    mo.chop(y, kit)
+    assert np.linalg.norm(y.e - s.e) / np.linalg.norm(s.e) < 1e-11
+
+
+def test_ihelm_inverts_del2_plus_alpha(kit3d):
+    kit = kit3d
+    rng = np.random.default_rng(8)
+    s = mo.scalar_init(kit, "FFF")
+    s.e[:] = (rng.standard_normal(s.e.shape) + 1j * rng.standard_normal(s.e.shape)) \
+        * np.exp(-np.arange(s.e.shape[0]) / 4.0)[:, None, None]
+    s.e[:, :, kit.p.nz // 2] = 0.0
+    mo.chop(s, kit)
+    alpha = -40.0                                  # -2 / (dt visc) of abcn is negative: del^2 + alpha is definite
+    x = s.copy()
+    mo.ihelm(x, alpha, kit)
+    y = x.copy()
+    mo.del2(y, kit)
+    y.e = y.e + alpha * x.e
+    mo.chop(y, kit)
+    assert np.linalg.norm(y.e - s.e) / np.linalg.norm(s.e) < 1e-12
+
+
+# ---- the semi-implicit integrators from their published discretisation ----------------------------------------------
+# docs/tutorial/time_integration.md:160-169, 381-390:  L = VISC del^2 - HYPERVISC (-del^2)^(HYPERPOW/2),
+#   febe:  w_{k+1} = w_k + dt A(w_k) + dt L(w_{k+1})
+#   abcn:  w_{k+1} = w_k + dt [1.5 A(w_k) - 0.5 A(w_{k-1})] + dt [0.5 L(w_{k+1}) + 0.5 L(w_k)]
+# The residual of those two equations is evaluated with L applied as repeated del2 (pinned above), not with the band
+# products and LAPACK factorisations the integrators themselves run.
+
+def _kit_with_viscosity(kit, visc, hyperpow, hypervisc):
+    from dataclasses import replace
+    p = replace(kit.p, visc=visc, hyperpow=hyperpow, hypervisc=hypervisc)
+    tables = dict(x=kit.x, w=kit.w, lognorm=kit.lognorm, pf=kit.pf, at0=kit.at0, at1=kit.at1)
+    return mo.kit_init(p, tables=tables)
+
+
+def _apply_L(s, kit):
+    """VISC del^2 s - HYPERVISC (-del^2)^(HYPERPOW/2) s, term by term."""
+    p = kit.p
+    a = s.copy()
+    mo.del2(a, kit)
+    out = p.visc * a.e
+    if p.hyperpow:
+        b = s.copy()
+        for _ in range(p.hyperpow // 2):
+            mo.del2(b, kit)
+            b.e = -b.e
+        out = out - p.hypervisc * b.e
+    return out
+
+
+def _smooth_field(kit, seed):
+    rng = np.random.default_rng(seed)
+    s = mo.scalar_init(kit, "FFF")
+    s.e[:] = (rng.standard_normal(s.e.shape) + 1j * rng.standard_normal(s.e.shape)) \
+        * np.exp(-np.arange(s.e.shape[0]) / 3.0)[:, None, None]
+    s.e[:, :, kit.p.nz // 2] = 0.0                 # the doubly visited Nyquist plane, see above
+    mo.chop(s, kit)
+    return s
+
+
+@pytest.mark.parametrize("visc,hyperpow,hypervisc", [(1.0e-2, 0, 0.0), (1.0e-3, 4, 1.0e-5), (1.0e-3, 8, 1.0e-9)])
+def test_febe_and_abcn_satisfy_the_published_discretisation(kit3d, visc, hyperpow, hypervisc):
+    kit = _kit_with_viscosity(kit3d, visc, hyperpow, hypervisc)
+    dt = 0.05
+    w0, nl, nl_p = _smooth_field(kit, 21), _smooth_field(kit, 22), _smooth_field(kit, 23)
+
+    w1 = w0.copy()
+    mo.febe(w1, nl, dt, kit)
+    res = w1.e - w0.e - dt * nl.e - dt * _apply_L(w1, kit)
+    r = mo.Scalar(e=np.asfortranarray(res), space="FFF")
+    mo.chop(r, kit)
+    assert np.linalg.norm(r.e) / np.linalg.norm(w1.e) < 1e-11
+
+    w1 = w0.copy()
+    w_prev, nl_prev = w0.copy(), nl_p.copy()
+    Lw0 = _apply_L(w0, kit)
+    mo.abcn(w1, w_prev, nl, nl_prev, dt, kit)
+    res = w1.e - w0.e - dt * (1.5 * nl.e - 0.5 * nl_p.e) - dt * (0.5 * _apply_L(w1, kit) + 0.5 * Lw0)
+    r = mo.Scalar(e=np.asfortranarray(res), space="FFF")
+    mo.chop(r, kit)
+    assert np.linalg.norm(r.e) / np.linalg.norm(w1.e) < 1e-11
+    # ops:1256: the previous-step slots receive the NEW field and the current nonlinear term
+    assert np.array_equal(w_prev.e, w1.e) and np.array_equal(nl_prev.e, nl.e)
