@@ -400,3 +400,51 @@ def test_febe_and_abcn_satisfy_the_published_discretisation(kit3d, visc, hyperpo
     assert np.linalg.norm(r.e) / np.linalg.norm(w1.e) < 1e-11
     # ops:1256: the previous-step slots receive the NEW field and the current nonlinear term
     assert np.array_equal(w_prev.e, w1.e) and np.array_equal(nl_prev.e, nl.e)
+
+
+def test_end_point_tables_are_the_closed_forms(kit3d):
+    """at0 / at1 (sinit:136-150: the m = 0 functions at x = -1 + 1e-15 and 1 - 1e-15) against P_n(-1) = (-1)^n,
+    P_n(1) = 1 with the orthonormal weight sqrt((2n+1)/2); the 1e-15 offset moves them by n(n+1)/2 * 1e-15."""
+    n = np.arange(kit3d.p.nrchop)
+    norm = np.sqrt((2.0 * n + 1.0) / 2.0)
+    assert np.max(np.abs(kit3d.at1 / norm - 1.0)) < 2e-12
+    assert np.max(np.abs(kit3d.at0 / norm - (-1.0) ** n)) < 2e-12
+    # calcat0 / calcat1 of a field = the synthesis of its m = 0 column at those points
+    s = mo.scalar_init(kit3d, "FFF")
+    s.e[:6, 0, 0] = [1.0, -0.5, 0.25, 2.0, 0.0, -1.0]
+    s.e[:6, 0, 1] = [0.5j, 1.0, 0.0, -1.0j, 0.25, 0.0]
+    c0, c1 = mo.calcat0(s, kit3d), mo.calcat1(s, kit3d)
+    for k in (0, 1):
+        col = s.e[:6, 0, k]
+        assert abs(c0[k] - np.sum(col * norm[:6] * (-1.0) ** n[:6])) < 1e-12
+        assert abs(c1[k] - np.sum(col * norm[:6])) < 1e-12
+    mo.zeroat1(s, kit3d)
+    assert np.max(np.abs(mo.calcat1(s, kit3d))) < 1e-14
+
+
+def test_delsqp_is_the_weighted_horizontal_laplacian(kit3d):
+    """docs/tutorial/operation.md:300-302: ((L^2 + r^2) / (2 L^2))^2 del_perp^2 P_{L_n}^m = -n(n+1)/L^2 P_{L_n}^m.  delsqp's
+    diagonal factors against the pinned del2h evaluated on the grid and weighted there, for low-degree content."""
+    kit = kit3d
+    rng = np.random.default_rng(31)
+    s = mo.scalar_init(kit, "FFF")
+    for m in range(6):
+        s.e[:8, m, :2] = rng.standard_normal((8, 2)) + 1j * rng.standard_normal((8, 2))
+    s.e[0, 0, :] = 0.0                              # n = 0: the logarithmic term's slot (ops:360)
+    a, b = s.copy(), s.copy()
+    mo.delsqp(a, kit)
+    mo.del2h(b, kit)
+    a.space = "FFP"
+    b.space = "FFP"
+    mo.rtrans_backward(a, kit)
+    mo.rtrans_backward(b, kit)
+    nr = kit.p.nr
+    wgt = ((kit.p.ell ** 2 + kit.r ** 2) / (2.0 * kit.p.ell ** 2)) ** 2
+    # compared unweighted: the weight reaches 1e6 at the outermost node and would only amplify del2h's rounding
+    lhs = a.e[:nr, :6, :2] / wgt[:, None, None]
+    rhs = b.e[:nr, :6, :2]
+    assert np.max(np.abs(lhs - rhs)) / np.max(np.abs(rhs)) < 1e-12
+    inv = s.copy()
+    mo.delsqp(inv, kit)
+    mo.idelsqp(inv, kit)
+    assert np.linalg.norm(inv.e - s.e) / np.linalg.norm(s.e) < 1e-14
