@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 
 from oracle import mlegs_oracle as mo
+import definition as dfn
 
 
 @pytest.fixture(scope="module")
@@ -131,85 +132,42 @@ def kit_small():
 
 
 @pytest.fixture(scope="module")
-def basis_small(kit_small):
-    return _basis_at_all_nodes(kit_small)
+def kit_mid():
+    # the lengths the register-resident FFT kernels of the device library start at (np/2 = nz = 32)
+    p = mo.Params(nr=32, np=64, nz=32, nrchop=32, npchop=5, nzchop=17, ell=4.0, zlen=2.0 * math.pi,
+                  visc=1.0e-3, hyperpow=0, hypervisc=0.0)
+    return mo.kit_init(p)
 
 
-def _basis_at_all_nodes(kit):
-    """B[i, j, m] = orthonormal P_{m+j}^m(x_i) at all nr nodes, from mpmath (30 digits)."""
-    mpmath.mp.dps = 30
-    nr, npc = kit.p.nr, kit.chopp
-    B = np.zeros((nr, kit.p.nrchop, npc))
-    for m in range(npc):
-        for j in range(int(kit.chops[m])):
-            n = m + j
-            norm = mpmath.sqrt(mpmath.mpf(2 * n + 1) / 2 * mpmath.factorial(n - m) / mpmath.factorial(n + m))
-            for i in range(nr):
-                B[i, j, m] = float(norm * mpmath.legenp(n, m, mpmath.mpf(float(kit.x[i])), type=2))
-    return B
-
-
-def _signed_k(nz):
-    k = np.arange(nz)
-    return np.where(k <= nz // 2, k, k - nz)     # FFT order: 0, 1, ..., nz/2, -(nz/2-1), ..., -1
-
-
-def test_synthesis_equals_the_published_triple_sum(kit_small, basis_small):
-    kit = kit_small
+def _from_definition_both_ways(kit, backend, tol):
     nr, npts, nz = kit.p.nr, kit.p.np, kit.p.nz
-    nph = npts // 2
-    rng = np.random.default_rng(11)
-    a = np.zeros(kit.glb_sz, dtype=complex)
-    for m in range(kit.chopp):
-        nn = int(kit.chops[m])
-        a[:nn, m, :nz] = rng.standard_normal((nn, nz)) + 1j * rng.standard_normal((nn, nz))
-    s = mo.Scalar(e=np.asfortranarray(a.copy()), space="FFF")
+    B = dfn.basis_at_all_nodes(kit.x, kit.p.nrchop, kit.chopp, backend)
+    # synthesis
+    a = dfn.random_triangular(kit.glb_sz, kit.p.nrchop, kit.chopp, nz, seed=11)
+    s = mo.Scalar(e=a.copy(order="F"), space="FFF")
     mo.trans(s, "PPP", kit)
-    got = s.e[:nr, :nph, :nz]
-    phys_got = np.empty((nr, npts, nz))
-    phys_got[:, 0::2, :] = got.real          # Re = phi_{2q}, Im = phi_{2q+1}
-    phys_got[:, 1::2, :] = got.imag
-
-    B = basis_small
-    kk = _signed_k(nz)
-    ez = np.exp(2j * np.pi * np.outer(kk, np.arange(nz)) / nz)          # [k, l]  exp(i kappa z_l), z_l = zlen l / nz
-    ephi = np.exp(2j * np.pi * np.outer(np.arange(kit.chopp), np.arange(npts)) / npts)   # [m, p]  exp(i m phi_p)
-    # c[i, m, l] = sum_k sum_j a[j, m, k] B[i, j, m] exp(i kappa z_l)
-    c = np.einsum("ijm,jmk,kl->iml", B, a[: kit.p.nrchop, : kit.chopp, :nz], ez)
-    # the field is real: the m < 0 terms are the conjugates of the m > 0 ones; m = 0 and the Nyquist m = np/2 appear once
-    want = np.zeros((nr, npts, nz))
-    for m in range(kit.chopp):
-        term = (c[:, m, None, :] * ephi[m][None, :, None]).real
-        want += term if m in (0, nph) else 2.0 * term
-    assert np.max(np.abs(phys_got - want)) / np.max(np.abs(want)) < 1e-13
-
-
-def test_analysis_equals_the_quadrature_of_the_definition(kit_small, basis_small):
-    kit = kit_small
-    nr, npts, nz = kit.p.nr, kit.p.np, kit.p.nz
-    nph = npts // 2
-    rng = np.random.default_rng(12)
-    phys = rng.standard_normal((nr, npts, nz))
-    e = np.zeros(kit.glb_sz, dtype=complex)
-    e[:nr, :nph, :nz] = phys[:, 0::2, :] + 1j * phys[:, 1::2, :]
-    s = mo.Scalar(e=np.asfortranarray(e), space="PPP")
+    want = dfn.synthesis_by_definition(a, B, npts, nz)
+    assert np.max(np.abs(dfn.unpack_ppp(s.e, nr, npts, nz) - want)) / np.max(np.abs(want)) < tol
+    # analysis
+    f = np.random.default_rng(12).standard_normal((nr, npts, nz))
+    s = mo.Scalar(e=dfn.pack_ppp(f, kit.glb_sz), space="PPP")
     mo.trans(s, "FFF", kit)
-
-    xg, wg = np.polynomial.legendre.leggauss(nr)          # third-party rule, matched to the kit's node order
-    order = np.argsort(kit.x)
-    w = np.empty(nr)
-    w[order] = wg
-    assert np.max(np.abs(kit.x[order] - xg)) < 4e-16
-    B = basis_small
-    kk = _signed_k(nz)
-    ez = np.exp(-2j * np.pi * np.outer(np.arange(nz), kk) / nz) / nz                       # [l, k]
-    ephi = np.exp(-2j * np.pi * np.outer(np.arange(npts), np.arange(kit.chopp)) / npts) / npts   # [p, m]
-    want = np.einsum("i,ijm,ipl,pm,lk->jmk", w, B, phys, ephi, ez)
+    want = dfn.analysis_by_definition(f, B, kit.x)
     got = s.e[: kit.p.nrchop, : kit.chopp, :nz]
     for m in range(kit.chopp):
         nn = int(kit.chops[m])
-        assert np.max(np.abs(got[:nn, m] - want[:nn, m])) / np.max(np.abs(want[:nn, m])) < 1e-13, m
+        assert np.max(np.abs(got[:nn, m] - want[:nn, m])) / np.max(np.abs(want[:nn, m])) < tol, m
         assert not np.any(got[nn:, m])                       # beyond the triangular truncation: exact zeros
+
+
+def test_transform_equals_the_published_triple_sum_mpmath(kit_small):
+    _from_definition_both_ways(kit_small, "mpmath", 1e-13)
+
+
+def test_transform_equals_the_published_triple_sum_scipy(kit_small, kit_mid):
+    # scipy's lpmv as the third-party Legendre function: fast enough for the size the GPU test of the same name runs
+    _from_definition_both_ways(kit_small, "scipy", 1e-12)
+    _from_definition_both_ways(kit_mid, "scipy", 1e-12)
 
 
 # ---- the toroidal-poloidal reconstruction from its published definition ---------------------------------------------
