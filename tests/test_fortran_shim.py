@@ -165,3 +165,65 @@ def test_the_submodule_implements_every_module_procedure_of_the_reference_interf
     assert len(want) >= 37
     assert want <= have, f"no body for {sorted(want - have)}"
     assert have <= want, f"bodies for procedures the interface does not declare: {sorted(have - want)}"
+
+
+def _call_sites(text):
+    """(name, [top-level argument strings]) of every mlegs_b200_* call in Fortran source text."""
+    out = []
+    for m in re.finditer(r"\b(mlegs_b200_[a-z0-9_]+)\s*\(", text):
+        i, depth, args, cur, quote = m.end(), 1, [], "", None
+        while depth and i < len(text):
+            ch = text[i]
+            if quote:
+                quote = None if ch == quote else quote
+                cur += ch
+            elif ch in "'\"":
+                quote = ch
+                cur += ch
+            elif ch == "(":
+                depth += 1
+                cur += ch
+            elif ch == ")":
+                depth -= 1
+                if depth:
+                    cur += ch
+            elif ch == "," and depth == 1:
+                args.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+            i += 1
+        if cur.strip():
+            args.append(cur.strip())
+        out.append((m.group(1), args))
+    return out
+
+
+def test_every_call_in_the_submodule_passes_the_declared_number_of_arguments():
+    ifaces = _fortran_interfaces()
+    text = "\n".join(_fortran_lines(F_SHIM))
+    sites = _call_sites(text)
+    assert len(sites) >= 35
+    for name, args in sites:
+        dummies, _ = ifaces[name]
+        assert len(args) == len(dummies), f"{name}: called with {len(args)} arguments {args}, declared with {dummies}"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_IFACE), reason="reference tree not present")
+def test_every_dummy_argument_of_the_reference_interface_is_used_by_its_body():
+    """A forwarding body that never mentions one of its dummies has dropped an argument (the kit `tfm` aside: the library
+    holds the kit it was initialised with)."""
+    ref = "\n".join(_fortran_lines(REF_IFACE))
+    decl = {m.group(1).lower(): [a.strip().lower() for a in m.group(2).split(",") if a.strip()]
+            for m in re.finditer(r"module\s+(?:recursive\s+)?(?:subroutine|function)\s+(\w+)\s*\(([^)]*)\)", ref, re.I)}
+    shim = "\n".join(_fortran_lines(F_SHIM))
+    bodies = {m.group(1).lower(): m.group(2).lower()
+              for m in re.finditer(r"module procedure\s+(\w+)(.*?)end procedure", shim, re.I | re.S)}
+    assert set(decl) == set(bodies)
+    for name, dummies in decl.items():
+        for d in dummies:
+            # axis_input: the recursion cursor of the reference's assemble/disassemble (one gather per distributed
+            # axis, dist:70-368); the slab layout has a single distributed axis and gathers it in one step
+            if d in ("tfm", "axis_input"):
+                continue
+            assert re.search(r"\b%s\b" % re.escape(d), bodies[name]), f"{name}: dummy `{d}` is never used"
